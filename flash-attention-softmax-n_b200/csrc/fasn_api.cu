@@ -1,0 +1,281 @@
+// C ABI of libfasn.so (declared in include/fasn.h): argument checking, TMA tensor-map construction, dispatch.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/fasn.h"
+#include "fasn_common.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+int fail_cuda(cudaError_t e, const char* what) {
+  return fail(static_cast<int>(e), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// (D, S, H, B) 16-bit tensor, box = 64 x 128 x 1 x 1, 128-byte swizzle, out-of-bounds rows read as zero.
+int make_map(CUtensorMap* m, const void* ptr, long long sb, long long sh, long long ss, int B, int H, int S, int D,
+             bool bf16, const char* name) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return fail(FASN_EDRIVER, "cuTensorMapEncodeTiled is not available from this driver");
+  if (ptr == nullptr) return fail(FASN_EINVAL, "%s: null pointer", name);
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(FASN_EUNSUPPORTED, "%s: pointer is not 16-byte aligned", name);
+  if (ss < D || (ss % 8) != 0) return fail(FASN_EUNSUPPORTED, "%s: row stride %lld must be >= head_dim and a multiple of 8 elements", name, ss);
+  // strides of size-1 axes are irrelevant to addressing: replace them by a packed value the encoder accepts
+  if (H == 1 || sh <= 0) { if (H != 1) return fail(FASN_EUNSUPPORTED, "%s: head stride must be positive", name); sh = (long long)S * ss; }
+  if (B == 1 || sb <= 0) { if (B != 1) return fail(FASN_EUNSUPPORTED, "%s: batch stride must be positive", name); sb = (long long)H * sh; }
+  if ((sh % 8) != 0 || (sb % 8) != 0) return fail(FASN_EUNSUPPORTED, "%s: head/batch strides must be multiples of 8 elements", name);
+  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ss * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {64, 128, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FASN_EDRIVER, "%s: cuTensorMapEncodeTiled failed with CUresult %d", name, (int)r);
+  return 0;
+}
+
+int check_common(const FasnParams* p) {
+  if (p == nullptr) return fail(FASN_EINVAL, "params is null");
+  if (p->struct_size != sizeof(FasnParams)) return fail(FASN_EINVAL, "struct_size %u != sizeof(FasnParams) %zu", p->struct_size, sizeof(FasnParams));
+  if (p->dtype != FASN_FP16 && p->dtype != FASN_BF16) return fail(FASN_EUNSUPPORTED, "dtype %u: only fp16 (0) and bf16 (1)", p->dtype);
+  if (p->head_dim != 64 && p->head_dim != 128) return fail(FASN_EUNSUPPORTED, "head_dim %d: only 64 and 128", p->head_dim);
+  if (p->batch <= 0 || p->heads <= 0 || p->seqlen_q <= 0 || p->seqlen_kv <= 0) return fail(FASN_EINVAL, "batch/heads/seqlen must be positive");
+  if (p->heads_kv != p->heads && p->heads_kv != 1) return fail(FASN_EINVAL, "heads_kv must equal heads or 1");
+  if ((long long)p->batch * p->heads > 65535) return fail(FASN_EUNSUPPORTED, "batch*heads > 65535 per call: shard the batch x head axis");
+  if (!(p->softmax_n >= 0.f)) return fail(FASN_EINVAL, "softmax_n must be >= 0");
+  if (!(p->dropout_p >= 0.f && p->dropout_p < 1.f)) return fail(FASN_EINVAL, "dropout_p must be in [0,1)");
+  if (!std::isfinite(p->scale)) return fail(FASN_EINVAL, "scale must be finite");
+  if (p->lse == nullptr) return fail(FASN_EINVAL, "lse is null");
+  return 0;
+}
+
+fasn::AuxView aux_view(const FasnAux& a) { return fasn::AuxView{a.ptr, a.stride_b, a.stride_h, a.stride_q}; }
+fasn::TensorView tensor_view(const FasnTensor& t) { return fasn::TensorView{t.ptr, t.stride_b, t.stride_h, t.stride_s}; }
+
+uint32_t keep_threshold(float dropout_p) {
+  long t = lroundf((1.0f - dropout_p) * 256.0f);
+  if (t < 0) t = 0;
+  if (t > 256) t = 256;
+  return (uint32_t)t;
+}
+
+fasn::PhiloxKey philox_key(uint64_t seed, uint64_t offset) {
+  return fasn::PhiloxKey{(uint32_t)(seed & 0xFFFFFFFFull), (uint32_t)(seed >> 32), (uint32_t)(offset & 0xFFFFFFFFull)};
+}
+
+}  // namespace
+
+extern "C" {
+
+int fasn_version(void) { return FASN_ABI_VERSION; }
+
+const char* fasn_last_error(void) { return g_last_error.c_str(); }
+
+int fasn_fwd(const FasnParams* p) {
+  if (int rc = check_common(p)) return rc;
+  const bool bf16 = p->dtype == FASN_BF16;
+  const int B = p->batch, H = p->heads, Hkv = p->heads_kv, L = p->seqlen_q, S = p->seqlen_kv, D = p->head_dim;
+  CUtensorMap tq, tk, tv, to;
+  if (int rc = make_map(&tq, p->q.ptr, p->q.stride_b, p->q.stride_h, p->q.stride_s, B, H, L, D, bf16, "q")) return rc;
+  if (int rc = make_map(&tk, p->k.ptr, p->k.stride_b, p->k.stride_h, p->k.stride_s, B, Hkv, S, D, bf16, "k")) return rc;
+  if (int rc = make_map(&tv, p->v.ptr, p->v.stride_b, p->v.stride_h, p->v.stride_s, B, Hkv, S, D, bf16, "v")) return rc;
+  if (int rc = make_map(&to, p->o.ptr, p->o.stride_b, p->o.stride_h, p->o.stride_s, B, H, L, D, bf16, "o")) return rc;
+  fasn::FwdArgs a{};
+  a.B = B; a.H = H; a.Hkv = Hkv; a.Sq = L; a.Skv = S;
+  a.causal_off = S - L;
+  a.scale_log2 = p->scale * fasn::kLog2e;
+  a.softmax_n = p->softmax_n;
+  a.lse = p->lse;
+  a.o = tensor_view(p->o);
+  a.mask = aux_view(p->mask);
+  a.bias = aux_view(p->bias);
+  a.drop_thr = keep_threshold(p->dropout_p);
+  a.inv_keep = 1.0f / (1.0f - p->dropout_p);
+  a.key = philox_key(p->philox_seed, p->philox_offset);
+  a.bh_offset = (uint32_t)p->bh_offset;
+  cudaError_t e = fasn::launch_fwd(D, bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tk, tv, to, a, (cudaStream_t)p->stream);
+  if (e != cudaSuccess) return fail_cuda(e, "fasn_fwd launch");
+  return 0;
+}
+
+int fasn_bwd_workspace(const FasnParams* p, uint64_t* delta_bytes, uint64_t* dq_accum_bytes) {
+  if (p == nullptr || delta_bytes == nullptr || dq_accum_bytes == nullptr) return fail(FASN_EINVAL, "null argument");
+  const uint64_t Lp = ((uint64_t)p->seqlen_q + 127) / 128 * 128;
+  *delta_bytes = 2ull * (uint64_t)p->batch * p->heads * Lp * sizeof(float);   // delta + LSE_n*log2e
+  *dq_accum_bytes = (uint64_t)p->batch * p->heads * Lp * p->head_dim * sizeof(float);
+  return 0;
+}
+
+int fasn_bwd(const FasnParams* p) {
+  if (int rc = check_common(p)) return rc;
+  if (p->delta == nullptr || p->dq_accum == nullptr) return fail(FASN_EINVAL, "delta / dq_accum workspace is null");
+  if (p->dq.ptr == nullptr) return fail(FASN_EINVAL, "dq is null");
+  const bool bf16 = p->dtype == FASN_BF16;
+  const int B = p->batch, H = p->heads, Hkv = p->heads_kv, L = p->seqlen_q, S = p->seqlen_kv, D = p->head_dim;
+  CUtensorMap tq, tk, tv, tdo, tdk, tdv;
+  if (int rc = make_map(&tq, p->q.ptr, p->q.stride_b, p->q.stride_h, p->q.stride_s, B, H, L, D, bf16, "q")) return rc;
+  if (int rc = make_map(&tk, p->k.ptr, p->k.stride_b, p->k.stride_h, p->k.stride_s, B, Hkv, S, D, bf16, "k")) return rc;
+  if (int rc = make_map(&tv, p->v.ptr, p->v.stride_b, p->v.stride_h, p->v.stride_s, B, Hkv, S, D, bf16, "v")) return rc;
+  if (int rc = make_map(&tdo, p->dout.ptr, p->dout.stride_b, p->dout.stride_h, p->dout.stride_s, B, H, L, D, bf16, "dout")) return rc;
+  if (int rc = make_map(&tdk, p->dk.ptr, p->dk.stride_b, p->dk.stride_h, p->dk.stride_s, B, H, S, D, bf16, "dk")) return rc;
+  if (int rc = make_map(&tdv, p->dv.ptr, p->dv.stride_b, p->dv.stride_h, p->dv.stride_s, B, H, S, D, bf16, "dv")) return rc;
+  if (p->o.ptr == nullptr) return fail(FASN_EINVAL, "o is null");
+  fasn::BwdArgs a{};
+  a.B = B; a.H = H; a.Hkv = Hkv; a.Sq = L; a.Skv = S;
+  a.causal_off = S - L;
+  a.scale = p->scale;
+  a.scale_log2 = p->scale * fasn::kLog2e;
+  a.lse = p->lse;
+  a.delta = p->delta;
+  a.dq_accum = p->dq_accum;
+  a.Sqp = (L + 127) / 128 * 128;
+  a.mask = aux_view(p->mask);
+  a.bias = aux_view(p->bias);
+  a.drop_thr = keep_threshold(p->dropout_p);
+  a.inv_keep = 1.0f / (1.0f - p->dropout_p);
+  a.key = philox_key(p->philox_seed, p->philox_offset);
+  a.bh_offset = (uint32_t)p->bh_offset;
+  cudaStream_t st = (cudaStream_t)p->stream;
+  cudaError_t e = fasn::launch_bwd_prep(D, bf16, tensor_view(p->o), tensor_view(p->dout), a, st);
+  if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd prep launch");
+  e = fasn::launch_bwd(D, bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tk, tv, tdo, tdk, tdv, a, tensor_view(p->dk), tensor_view(p->dv), st);
+  if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd main launch");
+  e = fasn::launch_bwd_finish(D, bf16, tensor_view(p->dq), a, st);
+  if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd finish launch");
+  return 0;
+}
+
+int fasn_dropout_mask(uint8_t* out, int32_t batch, int32_t heads, int32_t seqlen_q, int32_t seqlen_kv, float dropout_p,
+                      uint64_t philox_seed, uint64_t philox_offset, int64_t bh_offset, void* stream) {
+  if (out == nullptr || batch <= 0 || heads <= 0 || seqlen_q <= 0 || seqlen_kv <= 0) return fail(FASN_EINVAL, "bad argument");
+  if (!(dropout_p >= 0.f && dropout_p < 1.f)) return fail(FASN_EINVAL, "dropout_p must be in [0,1)");
+  cudaError_t e = fasn::launch_dropout_mask(out, batch, heads, seqlen_q, seqlen_kv, keep_threshold(dropout_p),
+                                            philox_key(philox_seed, philox_offset), (uint32_t)bh_offset, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(e, "fasn_dropout_mask launch");
+  return 0;
+}
+
+int fasn_probe(int mode, uint32_t dtype, const void* x, const void* y, float* c, void* stream) {
+  if (mode < 0 || mode > 3 || x == nullptr || y == nullptr || c == nullptr) return fail(FASN_EINVAL, "bad argument");
+  if (dtype != FASN_FP16 && dtype != FASN_BF16) return fail(FASN_EUNSUPPORTED, "dtype");
+  const bool bf16 = dtype == FASN_BF16;
+  CUtensorMap tx, ty;
+  if (int rc = make_map(&tx, x, 0, 0, 128, 1, 1, 128, 128, bf16, "x")) return rc;
+  if (int rc = make_map(&ty, y, 0, 0, 128, 1, 1, 128, 128, bf16, "y")) return rc;
+  cudaError_t e = fasn::launch_probe(mode, bf16, tx, ty, x, c, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(e, "fasn_probe launch");
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// host-buffer entry point (end-to-end measurement: H2D + kernels + D2H inside one call)
+// -------------------------------------------------------------------------------------------------
+namespace {
+struct Arena {
+  void* base = nullptr;
+  size_t cap = 0;
+  std::mutex mu;
+};
+Arena g_arena;
+}  // namespace
+
+int fasn_attention_host(uint32_t dtype, int32_t batch, int32_t heads, int32_t seqlen_q, int32_t seqlen_kv, int32_t head_dim,
+                        const void* q_host, const void* k_host, const void* v_host, void* o_host, const void* dout_host,
+                        void* dq_host, void* dk_host, void* dv_host, float softmax_n, float scale, int32_t is_causal,
+                        float dropout_p, uint64_t philox_seed, uint64_t philox_offset, void* stream) {
+  if (!q_host || !k_host || !v_host || !o_host) return fail(FASN_EINVAL, "null host pointer");
+  const bool bwd = dout_host != nullptr;
+  if (bwd && (!dq_host || !dk_host || !dv_host)) return fail(FASN_EINVAL, "backward requested but a gradient host pointer is null");
+  if (batch <= 0 || heads <= 0 || seqlen_q <= 0 || seqlen_kv <= 0 || (head_dim != 64 && head_dim != 128))
+    return fail(FASN_EINVAL, "bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t BH = (size_t)batch * heads;
+  const size_t Lp = ((size_t)seqlen_q + 127) / 128 * 128;
+  const size_t nq = BH * seqlen_q * head_dim * 2, nkv = BH * seqlen_kv * head_dim * 2;
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  // layout: q k v o lse | dout dq dk dv delta dq_accum
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += up(bytes); return o; };
+  const size_t o_q = take(nq), o_k = take(nkv), o_v = take(nkv), o_o = take(nq), o_lse = take(BH * seqlen_q * 4);
+  size_t o_do = 0, o_dq = 0, o_dk = 0, o_dv = 0, o_delta = 0, o_acc = 0;
+  if (bwd) {
+    o_do = take(nq); o_dq = take(nq); o_dk = take(nkv); o_dv = take(nkv); o_delta = take(2 * BH * Lp * 4);
+    o_acc = take(BH * Lp * head_dim * 4);
+  }
+  std::lock_guard<std::mutex> lock(g_arena.mu);
+  if (g_arena.cap < off) {
+    if (g_arena.base) cudaFree(g_arena.base);
+    g_arena.base = nullptr; g_arena.cap = 0;
+    cudaError_t e = cudaMalloc(&g_arena.base, off);
+    if (e != cudaSuccess) return fail_cuda(e, "arena cudaMalloc");
+    g_arena.cap = off;
+  }
+  char* base = static_cast<char*>(g_arena.base);
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(base + o_q, q_host, nq, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail_cuda(e, "H2D q");
+  if ((e = cudaMemcpyAsync(base + o_k, k_host, nkv, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail_cuda(e, "H2D k");
+  if ((e = cudaMemcpyAsync(base + o_v, v_host, nkv, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail_cuda(e, "H2D v");
+  if (bwd && (e = cudaMemcpyAsync(base + o_do, dout_host, nq, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail_cuda(e, "H2D dout");
+
+  FasnParams p;
+  memset(&p, 0, sizeof(p));
+  p.struct_size = sizeof(FasnParams);
+  p.dtype = dtype;
+  p.batch = batch; p.heads = heads; p.heads_kv = heads; p.seqlen_q = seqlen_q; p.seqlen_kv = seqlen_kv; p.head_dim = head_dim;
+  auto tv4 = [&](size_t o, int S) {
+    FasnTensor t; t.ptr = base + o; t.stride_s = head_dim; t.stride_h = (int64_t)S * head_dim; t.stride_b = (int64_t)heads * S * head_dim;
+    return t;
+  };
+  p.q = tv4(o_q, seqlen_q); p.k = tv4(o_k, seqlen_kv); p.v = tv4(o_v, seqlen_kv); p.o = tv4(o_o, seqlen_q);
+  p.lse = reinterpret_cast<float*>(base + o_lse);
+  p.softmax_n = softmax_n; p.scale = scale; p.is_causal = is_causal; p.dropout_p = dropout_p;
+  p.philox_seed = philox_seed; p.philox_offset = philox_offset; p.bh_offset = 0;
+  p.stream = stream;
+  if (int rc = fasn_fwd(&p)) return rc;
+  if ((e = cudaMemcpyAsync(o_host, base + o_o, nq, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail_cuda(e, "D2H o");
+  if (bwd) {
+    p.dout = tv4(o_do, seqlen_q); p.dq = tv4(o_dq, seqlen_q); p.dk = tv4(o_dk, seqlen_kv); p.dv = tv4(o_dv, seqlen_kv);
+    p.delta = reinterpret_cast<float*>(base + o_delta);
+    p.dq_accum = reinterpret_cast<float*>(base + o_acc);
+    if (int rc = fasn_bwd(&p)) return rc;
+    if ((e = cudaMemcpyAsync(dq_host, base + o_dq, nq, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail_cuda(e, "D2H dq");
+    if ((e = cudaMemcpyAsync(dk_host, base + o_dk, nkv, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail_cuda(e, "D2H dk");
+    if ((e = cudaMemcpyAsync(dv_host, base + o_dv, nkv, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail_cuda(e, "D2H dv");
+  }
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail_cuda(e, "stream synchronize");
+  return 0;
+}
+
+}  // extern "C"

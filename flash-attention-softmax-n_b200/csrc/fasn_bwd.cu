@@ -1,0 +1,452 @@
+// Backward kernel: dQ, dK, dV of attention-with-softmax_n for sm_100a.
+//
+// Replaces the reference's `_bwd_kernel` (flash_attention_softmax_n/core/flash_attn_triton.py:146-235), which runs
+// one program per head, serial over KV blocks, with a read-modify-write of dQ in HBM per inner iteration.  Here one
+// CTA owns one 128-row K/V tile of one (batch, head) unit and streams the 128-row Q/dO tiles past it, everything
+// transposed so that the probabilities land in TMEM as the A operand of the next MMA (no shared-memory round trip):
+//
+//   S^T  = K Q_i^T            SS-MMA, K-major operands              -> TMEM [0,128)
+//   dP^T = V dO_i^T           SS-MMA                                -> TMEM [128,256)
+//   P^T  = exp2(S^T c - LSE2_n[q])        compute warps, in registers; dropout mask regenerated from philox
+//   dS^T = P^T o (Z/(1-p) dP^T - delta[q])
+//   dV  += (P^T o Z/(1-p)) dO_i   TS-MMA, A = P^T in TMEM (16-bit, written over the first half of each thread's own
+//                                 S^T columns: [0,32) and [64,96)), B = dO_i MN-major        -> TMEM [256,256+D)
+//   dK  += dS^T Q_i               SS-MMA, A = dS^T in smem (K-major),    B = Q_i MN-major   -> TMEM [256+D,256+2D)
+//   dQ_i = dS K                   SS-MMA, A = the same smem tile read MN-major, B = K MN-major -> TMEM [128,128+D)
+//                                 (aliases dP^T), then reduced into the fp32 dq_accum with red.global.add.v4.f32
+//
+// The only difference from softmax_0 attention is that P is recomputed from LSE_n = ln(n + sum exp s) (SURVEY.md
+// section 9): the Jacobian keeps the softmax form dS = P o (dP - delta) with delta_i = sum_d O_id dO_id.
+//
+//   warps 0-7   compute: warp w owns TMEM lanes 32(w%4).. (kv rows) and q-columns 64(w/4)..64(w/4)+63
+//   warps 8-11  dQ reducers: TMEM -> registers -> red.global.add
+//   warp 12     TMA producer (K,V once; Q_i + LSE2 and dO_i + delta through 2-deep rings)
+//   warp 13     MMA issuer (one thread)        warp 14  TMEM allocator        warp 15  idle
+#include "fasn_common.cuh"
+#include "fasn_ptx.cuh"
+
+namespace fasn {
+
+namespace {
+
+constexpr int kBwdThreads = 512;
+
+template <int D> struct BwdCfg {
+  static constexpr int DB = D / 64;
+  static constexpr int TILE_BYTES = 128 * D * 2;
+  static constexpr int BLK_BYTES = 128 * 128;
+  static constexpr int DS_BYTES = 2 * BLK_BYTES;                  // dS^T: [2 q-blocks][128 kv rows][128 B]
+  static constexpr int NUM_BARS = 20;
+  // K, V, Q ring (2), dO ring (2), dS^T, LSE2 ring + delta ring (2 x 2 x 512 B), barriers, tmem slot
+  static constexpr int SMEM_BYTES = 6 * TILE_BYTES + DS_BYTES + 4 * 512 + NUM_BARS * 8 + 16;
+};
+
+// cp.async.bulk 1-D global -> shared with mbarrier completion
+FASN_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                const __grid_constant__ CUtensorMap tm_dk, const __grid_constant__ CUtensorMap tm_dv, const BwdArgs a,
+                const TensorView dk_view, const TensorView dv_view) {
+  using Cfg = BwdCfg<D>;
+  constexpr int DB = Cfg::DB, TILE_BYTES = Cfg::TILE_BYTES, BLK_BYTES = Cfg::BLK_BYTES;
+  constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 128, TM_DV = 256, TM_DK = 256 + D;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kt = blockIdx.x;
+  const int k0 = kt * 128;
+  const int bh = blockIdx.y;
+  const int b = bh / a.H;
+  const int h = bh - b * a.H;
+  const int hk = (a.Hkv == 1) ? 0 : h;
+
+  const int nq = (a.Sq + 127) >> 7;
+  int i_start = 0;
+  if (CAUSAL) {
+    const int first_q = k0 - a.causal_off;           // first query row that sees key k0
+    i_start = first_q > 0 ? (first_q >> 7) : 0;
+  }
+  const int n_iter = nq - i_start;
+
+  if (n_iter <= 0) {
+    // no query sees this K/V tile: dK = dV = 0
+    if (threadIdx.x < 128) {
+      const int row = k0 + threadIdx.x;
+      if (row < a.Skv) {
+        uint4* pk = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(dk_view.ptr) + b * dk_view.sb + h * dk_view.sh + (long long)row * dk_view.ss);
+        uint4* pv = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(dv_view.ptr) + b * dv_view.sb + h * dv_view.sh + (long long)row * dv_view.ss);
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) { pk[i] = make_uint4(0, 0, 0, 0); pv[i] = make_uint4(0, 0, 0, 0); }
+      }
+    }
+    return;
+  }
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();      // 128B-swizzled tiles need 1024-byte alignment
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + TILE_BYTES;
+  uint8_t* sQ = sV + TILE_BYTES;              // [2]
+  uint8_t* sDO = sQ + 2 * TILE_BYTES;         // [2]
+  uint8_t* sDS = sDO + 2 * TILE_BYTES;
+  float* sLse = reinterpret_cast<float*>(sDS + Cfg::DS_BYTES);   // [2][128]
+  float* sDelta = sLse + 256;                                    // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;     // [2]
+  uint64_t* q_empty = bars + 3;    // [2]
+  uint64_t* do_full = bars + 5;    // [2]
+  uint64_t* do_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* dp_full = bars + 10;
+  uint64_t* p_full = bars + 11;    // 256 arrivals
+  uint64_t* ds_full = bars + 12;   // 256 arrivals
+  uint64_t* ds_empty = bars + 13;
+  uint64_t* dq_full = bars + 14;
+  uint64_t* dq_empty = bars + 15;  // 128 arrivals
+  uint64_t* dkv_full = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NUM_BARS);
+
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dk); tma_prefetch_desc(&tm_dv);
+  }
+  if (warp == 13 && lane == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&do_full[i], 1); mbar_init(&do_empty[i], 1); }
+    mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(ds_empty, 1);
+    mbar_init(dq_full, 1); mbar_init(dq_empty, 128); mbar_init(dkv_full, 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 14) { tmem_alloc<512>(tmem_slot); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 12) {
+    setmaxnreg_dec<56>();
+    if (warp == 12 && lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
+#pragma unroll
+      for (int db = 0; db < DB; ++db) {
+        tma_load_4d(sK + db * BLK_BYTES, &tm_k, kv_full, db * 64, k0, hk, b);
+        tma_load_4d(sV + db * BLK_BYTES, &tm_v, kv_full, db * 64, k0, hk, b);
+      }
+      const float* lse2 = a.delta + (long long)a.B * a.H * a.Sqp;     // second half of the workspace
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int qi0 = (i_start + it) * 128;
+        mbar_wait(&q_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&q_full[s], TILE_BYTES + 512);
+#pragma unroll
+        for (int db = 0; db < DB; ++db) tma_load_4d(sQ + s * TILE_BYTES + db * BLK_BYTES, &tm_q, &q_full[s], db * 64, qi0, h, b);
+        bulk_load_1d(sLse + s * 128, lse2 + (long long)bh * a.Sqp + qi0, 512, &q_full[s]);
+        mbar_wait(&do_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&do_full[s], TILE_BYTES + 512);
+#pragma unroll
+        for (int db = 0; db < DB; ++db) tma_load_4d(sDO + s * TILE_BYTES + db * BLK_BYTES, &tm_do, &do_full[s], db * 64, qi0, h, b);
+        bulk_load_1d(sDelta + s * 128, a.delta + (long long)bh * a.Sqp + qi0, 512, &do_full[s]);
+      }
+    } else if (warp == 13 && lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc_kk = umma_idesc(BF16, 128, 128, false, false);   // S^T, dP^T
+      constexpr uint32_t idesc_dv = umma_idesc(BF16, 128, D, false, true);      // A in TMEM, B MN-major
+      constexpr uint32_t idesc_dk = umma_idesc(BF16, 128, D, false, true);      // A K-major smem, B MN-major
+      constexpr uint32_t idesc_dq = umma_idesc(BF16, 128, D, true, true);       // A, B MN-major
+      const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV), sQ_u = smem_u32(sQ), sDO_u = smem_u32(sDO), sDS_u = smem_u32(sDS);
+      auto issue_kmajor = [&](uint32_t tm_dst, uint32_t a_u, uint32_t b_u) {    // D[128x128] = A B^T over K = head dim
+#pragma unroll
+        for (int kb = 0; kb < D / 16; ++kb) {
+          const uint32_t off = (kb >> 2) * BLK_BYTES + (kb & 3) * 32;
+          umma_ss(tmem_base + tm_dst, umma_smem_desc(a_u + off, 16, 1024), umma_smem_desc(b_u + off, 16, 1024), idesc_kk, kb > 0 ? 1u : 0u);
+        }
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(&q_full[0], 0);
+      tc_fence_after();
+      issue_kmajor(TM_S, sK_u, sQ_u);
+      tc_commit(s_full);
+      mbar_wait(&do_full[0], 0);
+      tc_fence_after();
+      issue_kmajor(TM_DP, sV_u, sDO_u);
+      tc_commit(dp_full);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it & 1;
+        const int s1 = s ^ 1;
+        const uint32_t ph1 = ((it + 1) >> 1) & 1;
+        const bool more = it + 1 < n_iter;
+        // dV += P^T dO_i
+        mbar_wait(p_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb)
+          umma_ts(tmem_base + TM_DV, tmem_base + TM_S + (kb >> 2) * 64 + (kb & 3) * 8,
+                  umma_smem_desc(sDO_u + s * TILE_BYTES + kb * 2048, BLK_BYTES, 1024), idesc_dv, (it > 0 || kb > 0) ? 1u : 0u);
+        // S^T of the next Q tile (overwrites P^T: ordered behind the dV MMAs on the tensor pipe)
+        if (more) {
+          mbar_wait(&q_full[s1], ph1);
+          tc_fence_after();
+          issue_kmajor(TM_S, sK_u, sQ_u + s1 * TILE_BYTES);
+          tc_commit(s_full);
+        }
+        // dK += dS^T Q_i ;  dQ_i = dS K
+        mbar_wait(ds_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) {
+          const uint32_t off = (kb >> 2) * BLK_BYTES + (kb & 3) * 32;
+          umma_ss(tmem_base + TM_DK, umma_smem_desc(sDS_u + off, 16, 1024),
+                  umma_smem_desc(sQ_u + s * TILE_BYTES + kb * 2048, BLK_BYTES, 1024), idesc_dk, (it > 0 || kb > 0) ? 1u : 0u);
+        }
+        tc_commit(&q_empty[s]);      // Q_i, LSE2_i, dO_i and delta_i stay valid until the compute warps are done with
+        tc_commit(&do_empty[s]);     // tile i (ds_full above) and the MMAs that read them have completed
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb)
+          umma_ss(tmem_base + TM_DQ, umma_smem_desc(sDS_u + kb * 2048, BLK_BYTES, 1024), umma_smem_desc(sK_u + kb * 2048, BLK_BYTES, 1024),
+                  idesc_dq, kb > 0 ? 1u : 0u);
+        tc_commit(dq_full);
+        tc_commit(ds_empty);
+        // dP^T of the next tile reuses the dQ columns: wait until the reducers have drained dQ_i
+        if (more) {
+          mbar_wait(&do_full[s1], ph1);
+          mbar_wait(dq_empty, it & 1);
+          tc_fence_after();
+          issue_kmajor(TM_DP, sV_u, sDO_u + s1 * TILE_BYTES);
+          tc_commit(dp_full);
+        }
+      }
+      tc_commit(dkv_full);
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ dQ reducers
+    setmaxnreg_dec<104>();
+    const int r = (warp & 3) * 32 + lane;                 // query row inside the tile
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    for (int it = 0; it < n_iter; ++it) {
+      const int qrow = (i_start + it) * 128 + r;
+      float* dst = a.dq_accum + ((long long)bh * a.Sqp + qrow) * D;
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int hb = 0; hb < D / 64; ++hb) {
+        uint32_t v[64];
+        tmem_ld_x32(tmem_base + lane_off + TM_DQ + hb * 64, v);
+        tmem_ld_x32(tmem_base + lane_off + TM_DQ + hb * 64 + 32, v + 32);
+        tmem_wait_ld();
+        if (hb == D / 64 - 1) { tc_fence_before(); mbar_arrive(dq_empty); }
+        if (qrow < a.Sq) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 4)
+            red_add_v4(dst + hb * 64 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        }
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- compute warps
+    setmaxnreg_inc<176>();
+    const int quarter = warp & 3;
+    const int half = warp >> 2;
+    const int r = quarter * 32 + lane;                     // kv row inside the tile
+    const int kv_row = k0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t lane_bit = 1u << lane;
+    const bool kv_valid = kv_row < a.Skv;
+    const bool has_aux = (a.mask.ptr != nullptr) || (a.bias.ptr != nullptr);
+    const int kv_c = min(kv_row, a.Skv - 1);
+    const uint8_t* mbase = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr) + b * a.mask.sb + h * a.mask.sh + kv_c : nullptr;
+    const uint16_t* bbase = a.bias.ptr ? reinterpret_cast<const uint16_t*>(a.bias.ptr) + b * a.bias.sb + h * a.bias.sh + kv_c : nullptr;
+    const uint32_t bh_global = a.bh_offset + bh;
+    const uint32_t kvw = (uint32_t)(kv_row >> 5);          // identical for the 32 lanes of this warp
+
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int qi0 = (i_start + it) * 128;
+      const int qc0 = qi0 + half * 64;                     // first query column of this thread
+      uint32_t kw0 = 0xFFFFFFFFu, kw1 = 0xFFFFFFFFu;
+      if constexpr (DROPOUT) {
+        // lane L generates the keep words of query rows qc0+L and qc0+32+L (all 32 kv rows of this warp)
+        kw0 = dropout_keep_word(a.key, bh_global, (uint32_t)(qc0 + lane), kvw, a.drop_thr);
+        kw1 = dropout_keep_word(a.key, bh_global, (uint32_t)(qc0 + 32 + lane), kvw, a.drop_thr);
+      }
+      // ---- P^T
+      mbar_wait(&q_full[s], ph);          // LSE2 of this tile has landed (same barrier as Q_i)
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      float p[64];
+      {
+        uint32_t* pr = reinterpret_cast<uint32_t*>(p);
+        tmem_ld_x32(tmem_base + lane_off + TM_S + half * 64, pr);
+        tmem_ld_x32(tmem_base + lane_off + TM_S + half * 64 + 32, pr + 32);
+        tmem_wait_ld();
+      }
+      const float* lse_s = sLse + s * 128 + half * 64;
+      const bool diag = CAUSAL && (qi0 + a.causal_off < k0 + 127);     // some (q, kv) of this tile pair is above the diagonal
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+        const float4 l4 = *reinterpret_cast<const float4*>(lse_s + c);
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float x = p[c + u] * a.scale_log2;
+          if (has_aux) {
+            const long long q_c = min(qc0 + c + u, a.Sq - 1);
+            if (bbase) x = fmaf(cvt16_to_f32<BF16>(bbase[q_c * a.bias.sq]), kLog2e, x);
+            if (mbase && mbase[q_c * a.mask.sq] == 0) x = -INFINITY;
+          }
+          float e = ex2(x - lv[u]);
+          bool ok = kv_valid;
+          if (diag) ok = ok && (kv_row <= qc0 + c + u + a.causal_off);
+          p[c + u] = ok ? e : 0.f;
+        }
+      }
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+          float x0 = p[c], x1 = p[c + 1];
+          if constexpr (DROPOUT) {
+            const uint32_t w0 = __shfl_sync(0xffffffffu, (c < 32) ? kw0 : kw1, c & 31);
+            const uint32_t w1 = __shfl_sync(0xffffffffu, (c < 32) ? kw0 : kw1, (c + 1) & 31);
+            x0 = (w0 & lane_bit) ? x0 * a.inv_keep : 0.f;
+            x1 = (w1 & lane_bit) ? x1 * a.inv_keep : 0.f;
+          }
+          pk[c >> 1] = pack2<BF16>(x0, x1);
+        }
+        tmem_st_x32(tmem_base + lane_off + TM_S + half * 64, pk);   // over this thread's own S^T columns only
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      mbar_arrive(p_full);
+      // ---- dS^T
+      mbar_wait(&do_full[s], ph);         // delta of this tile has landed (same barrier as dO_i)
+      mbar_wait(dp_full, it & 1);
+      tc_fence_after();
+      mbar_wait(ds_empty, (it & 1) ^ 1);  // MMAs of the previous iteration no longer read the dS^T tile
+      const float* del_s = sDelta + s * 128 + half * 64;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t dpr[32];
+        tmem_ld_x32(tmem_base + lane_off + TM_DP + half * 64 + g * 32, dpr);
+        tmem_wait_ld();
+        uint32_t out[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(del_s + g * 32 + c);
+          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+          float ds[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float dp = __uint_as_float(dpr[c + u]);
+            if constexpr (DROPOUT) {
+              const uint32_t w = __shfl_sync(0xffffffffu, (g == 0) ? kw0 : kw1, c + u);
+              dp = (w & lane_bit) ? dp * a.inv_keep : 0.f;
+            }
+            ds[u] = p[g * 32 + c + u] * (dp - dv[u]);
+          }
+          out[(c >> 1)] = pack2<BF16>(ds[0], ds[1]);
+          out[(c >> 1) + 1] = pack2<BF16>(ds[2], ds[3]);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int cc = g * 4 + q4;
+          *reinterpret_cast<uint4*>(sDS + half * BLK_BYTES + r * 128 + ((cc ^ (r & 7)) << 4)) =
+              make_uint4(out[q4 * 4], out[q4 * 4 + 1], out[q4 * 4 + 2], out[q4 * 4 + 3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(ds_full);
+    }
+
+    // ------------------------------------------------------------------ dK, dV epilogue
+    mbar_wait(dkv_full, 0);
+    tc_fence_after();
+    // K and V tiles are dead now: stage dK into sK and dV into sV (same swizzled [block][row][128 B] layout)
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      uint8_t* stage = which == 0 ? sV : sK;
+      const uint32_t tm_src = which == 0 ? TM_DV : TM_DK;
+      const float mul = which == 0 ? 1.f : a.scale;
+      constexpr int COLS = D / 2;                          // columns per thread (this warp's half)
+#pragma unroll
+      for (int cb = 0; cb < COLS / 32; ++cb) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + lane_off + tm_src + half * COLS + cb * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          w.x = pack2<BF16>(__uint_as_float(v[g * 8 + 0]) * mul, __uint_as_float(v[g * 8 + 1]) * mul);
+          w.y = pack2<BF16>(__uint_as_float(v[g * 8 + 2]) * mul, __uint_as_float(v[g * 8 + 3]) * mul);
+          w.z = pack2<BF16>(__uint_as_float(v[g * 8 + 4]) * mul, __uint_as_float(v[g * 8 + 5]) * mul);
+          w.w = pack2<BF16>(__uint_as_float(v[g * 8 + 6]) * mul, __uint_as_float(v[g * 8 + 7]) * mul);
+          const int col = half * COLS + cb * 32 + g * 8;
+          const int db = col >> 6;
+          const int cc = (col & 63) >> 3;
+          *reinterpret_cast<uint4*>(stage + db * BLK_BYTES + r * 128 + ((cc ^ (r & 7)) << 4)) = w;
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 256);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int db = 0; db < DB; ++db) {
+        tma_store_4d(&tm_dv, sV + db * BLK_BYTES, db * 64, k0, h, b);
+        tma_store_4d(&tm_dk, sK + db * BLK_BYTES, db * 64, k0, h, b);
+      }
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 14) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
+static cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                                const CUtensorMap& tdk, const CUtensorMap& tdv, const BwdArgs& a, const TensorView& dk,
+                                const TensorView& dv, cudaStream_t stream) {
+  auto kern = fasn_bwd_kernel<D, BF16, CAUSAL, DROPOUT>;
+  constexpr int smem = BwdCfg<D>::SMEM_BYTES;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((a.Skv + 127) / 128, a.B * a.H, 1);
+  kern<<<grid, kBwdThreads, smem, stream>>>(tq, tk, tv, tdo, tdk, tdv, a, dk, dv);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bwd(int head_dim, bool bf16, bool causal, bool dropout, const CUtensorMap& tq, const CUtensorMap& tk,
+                       const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
+                       const BwdArgs& a, const TensorView& dk, const TensorView& dv, cudaStream_t stream) {
+#define FASN_BWD_CASE(D_, BF_, C_, DR_) \
+  if (head_dim == D_ && bf16 == BF_ && causal == C_ && dropout == DR_) return launch_bwd_t<D_, BF_, C_, DR_>(tq, tk, tv, tdo, tdk, tdv, a, dk, dv, stream);
+  FASN_BWD_CASE(64, false, false, false) FASN_BWD_CASE(64, false, false, true)
+  FASN_BWD_CASE(64, false, true, false)  FASN_BWD_CASE(64, false, true, true)
+  FASN_BWD_CASE(64, true, false, false)  FASN_BWD_CASE(64, true, false, true)
+  FASN_BWD_CASE(64, true, true, false)   FASN_BWD_CASE(64, true, true, true)
+  FASN_BWD_CASE(128, false, false, false) FASN_BWD_CASE(128, false, false, true)
+  FASN_BWD_CASE(128, false, true, false)  FASN_BWD_CASE(128, false, true, true)
+  FASN_BWD_CASE(128, true, false, false)  FASN_BWD_CASE(128, true, false, true)
+  FASN_BWD_CASE(128, true, true, false)   FASN_BWD_CASE(128, true, true, true)
+#undef FASN_BWD_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace fasn

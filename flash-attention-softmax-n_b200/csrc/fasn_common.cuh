@@ -1,0 +1,69 @@
+// Internal argument blocks shared by the kernels and the C-ABI translation unit.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "fasn_philox.cuh"
+
+namespace fasn {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct AuxView {          // dense mask / bias, element (b,h,i,j) at ptr[b*sb + h*sh + i*sq + j]
+  const void* ptr;
+  long long sb, sh, sq;
+};
+
+struct TensorView {       // (B,H,S,D) view, element strides, unit stride on D
+  void* ptr;
+  long long sb, sh, ss;
+};
+
+struct FwdArgs {
+  int B, H, Hkv, Sq, Skv;
+  int causal_off;         // Skv - Sq (bottom-right alignment)
+  float scale_log2;       // scale * log2(e)
+  float softmax_n;        // n
+  float* lse;             // (B,H,Sq)
+  TensorView o;           // only used by the "no visible keys" early-out
+  AuxView mask, bias;
+  uint32_t drop_thr;      // keep iff u8 < drop_thr
+  float inv_keep;         // 1/(1-p)
+  PhiloxKey key;
+  uint32_t bh_offset;
+};
+
+struct BwdArgs {
+  int B, H, Hkv, Sq, Skv;
+  int causal_off;
+  float scale;            // logit scale (natural units)
+  float scale_log2;       // scale * log2(e)
+  const float* lse;       // (B,H,Sq) natural log
+  const float* delta;     // workspace: [0] delta (B,H,Sqp), [1] LSE_n * log2e (B,H,Sqp), written by the prep kernel
+  float* dq_accum;        // (B,H,Sqp,D) fp32
+  int Sqp;                // Sq rounded up to 128
+  AuxView mask, bias;
+  uint32_t drop_thr;
+  float inv_keep;
+  PhiloxKey key;
+  uint32_t bh_offset;
+};
+
+// launchers implemented in the kernel translation units
+cudaError_t launch_fwd(int head_dim, bool bf16, bool causal, bool dropout, const CUtensorMap& tq, const CUtensorMap& tk,
+                       const CUtensorMap& tv, const CUtensorMap& to, const FwdArgs& a, cudaStream_t stream);
+
+cudaError_t launch_bwd_prep(int head_dim, bool bf16, const TensorView& o, const TensorView& dout, const BwdArgs& a,
+                            cudaStream_t stream);
+cudaError_t launch_bwd(int head_dim, bool bf16, bool causal, bool dropout, const CUtensorMap& tq, const CUtensorMap& tk,
+                       const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
+                       const BwdArgs& a, const TensorView& dk, const TensorView& dv, cudaStream_t stream);
+cudaError_t launch_bwd_finish(int head_dim, bool bf16, const TensorView& dq, const BwdArgs& a, cudaStream_t stream);
+
+cudaError_t launch_dropout_mask(uint8_t* out, int B, int H, int Sq, int Skv, uint32_t thr, PhiloxKey key,
+                                uint32_t bh_offset, cudaStream_t stream);
+cudaError_t launch_probe(int mode, bool bf16, const CUtensorMap& tx, const CUtensorMap& ty, const void* x, float* c,
+                         cudaStream_t stream);
+
+}  // namespace fasn

@@ -1,0 +1,380 @@
+// Forward kernel: O = dropout(softmax_n(scale Q K^T + bias, masked)) V for sm_100a.
+//
+// Replaces the reference's `_fwd_kernel` (flash_attention_softmax_n/core/flash_attn_triton.py:30-126) and the
+// SDPA call of `flash_attention_n` (flash_attention_softmax_n/core/flash_attn.py:115-124).
+//
+// One CTA owns 256 query rows (two 128-row tiles, "ping-pong") of one (batch, head) unit and streams the
+// 128-row K/V tiles past them:
+//
+//   warp 8      TMA producer   Q tiles once, K/V tiles through an NS-deep shared-memory ring (128B swizzle)
+//   warp 9      MMA issuer     S_t = Q_t K_j^T  (tcgen05.mma, operands in smem, accumulator in TMEM)
+//                              O_t += P_t V_j   (A = P_t read straight from TMEM, B = V_j MN-major in smem)
+//   warps 0-3   softmax, tile 0   one thread per query row: tcgen05.ld S, online softmax_n in the log2
+//   warps 4-7   softmax, tile 1   domain, P (16-bit) written back over S with tcgen05.st; epilogue
+//
+// softmax_n costs nothing per tile: the "+n" of the denominator is a virtual key with logit 0, weight n and
+// value 0, i.e. the running (max, sum) start at (0, n) instead of (-inf, 0).  This equals the reference's n
+// zero-padded K/V rows (flash_attn.py:66-67) for integer n and its epilogue acc/(n exp(-m) + l)
+// (flash_attn_triton.py:114) for real n, without the overflow of exp(-m).
+//
+// The running max is only moved when it grows by more than 2^8 (lazy rescale), so the O accumulator in TMEM is
+// rescaled rarely; exponent arguments stay <= 8 and P fits fp16/bf16.
+//
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D);  P_t aliases the first 64 columns of S_t.
+#include "fasn_common.cuh"
+#include "fasn_ptx.cuh"
+
+namespace fasn {
+
+namespace {
+
+constexpr int kFwdThreads = 384;
+constexpr float kRescaleThreshold = 8.0f;   // log2 units
+
+template <int D> struct FwdCfg {
+  static constexpr int NS = (D == 128) ? 2 : 4;          // K/V ring depth
+  static constexpr int DB = D / 64;                      // 128-byte blocks per row
+  static constexpr int TILE_BYTES = 128 * D * 2;
+  static constexpr int BLK_BYTES = 128 * 128;
+  static constexpr int NUM_BARS = 8 + 4 * NS;
+  static constexpr int SMEM_BYTES = 1024 + (2 + 2 * NS) * TILE_BYTES + NUM_BARS * 8 + 16;
+};
+
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const FwdArgs a) {
+  using Cfg = FwdCfg<D>;
+  constexpr int NS = Cfg::NS, DB = Cfg::DB, TILE_BYTES = Cfg::TILE_BYTES, BLK_BYTES = Cfg::BLK_BYTES;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qb = CAUSAL ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;   // heavy causal blocks first
+  const int q0 = qb * 256;
+  const int bh = blockIdx.y;
+  const int b = bh / a.H;
+  const int h = bh - b * a.H;
+  const int hk = (a.Hkv == 1) ? 0 : h;
+
+  // keys visible to this CTA: [0, kv_end)
+  int kv_end = a.Skv;
+  if (CAUSAL) kv_end = min(a.Skv, min(q0 + 256, a.Sq) + a.causal_off);
+  kv_end = max(kv_end, 0);
+  const int n_tiles = (kv_end + 127) >> 7;
+
+  if (n_tiles == 0) {
+    // No key is visible to any row of this block: softmax_n gives exactly 0 (n > 0), defined 0 for n == 0.
+    if (threadIdx.x < 256) {
+      const int row = q0 + threadIdx.x;
+      if (row < a.Sq) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.o.ptr) + b * a.o.sb + h * a.o.sh +
+                                              (long long)row * a.o.ss);
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
+        a.lse[(long long)bh * a.Sq + row] = (a.softmax_n > 0.f) ? logf(a.softmax_n) : INFINITY;
+      }
+    }
+    return;
+  }
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 2 * TILE_BYTES;
+  uint8_t* sV = sK + NS * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NS * TILE_BYTES);
+  uint64_t* q_full = bars;               // [2]
+  uint64_t* s_full = bars + 2;           // [2]
+  uint64_t* p_full = bars + 4;           // [2]
+  uint64_t* o_full = bars + 6;           // [2]
+  uint64_t* k_full = bars + 8;           // [NS]
+  uint64_t* k_empty = k_full + NS;       // [NS]
+  uint64_t* v_full = k_empty + NS;       // [NS]
+  uint64_t* v_empty = v_full + NS;       // [NS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NUM_BARS);
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o);
+  }
+  if (warp == 9 && lane == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 10) { tmem_alloc<512>(tmem_slot); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+    setmaxnreg_dec<64>();
+    if (warp == 8) {
+      // ------------------------------------------------------------------ TMA producer
+      if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
+#pragma unroll
+          for (int db = 0; db < DB; ++db)
+            tma_load_4d(sQ + t * TILE_BYTES + db * BLK_BYTES, &tm_q, &q_full[t], db * 64, q0 + t * 128, h, b);
+        }
+        for (int j = 0; j < n_tiles; ++j) {
+          const int s = j % NS;
+          const uint32_t ph = (j / NS) & 1;
+          mbar_wait(&k_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
+#pragma unroll
+          for (int db = 0; db < DB; ++db)
+            tma_load_4d(sK + s * TILE_BYTES + db * BLK_BYTES, &tm_k, &k_full[s], db * 64, j * 128, hk, b);
+          mbar_wait(&v_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
+#pragma unroll
+          for (int db = 0; db < DB; ++db)
+            tma_load_4d(sV + s * TILE_BYTES + db * BLK_BYTES, &tm_v, &v_full[s], db * 64, j * 128, hk, b);
+        }
+      }
+    } else if (warp == 9) {
+      // ------------------------------------------------------------------ MMA issuer (one thread)
+      if (lane == 0) {
+        constexpr uint32_t idesc_qk = umma_idesc(BF16, 128, 128, false, false);
+        constexpr uint32_t idesc_pv = umma_idesc(BF16, 128, D, false, true);
+        const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+        auto issue_qk = [&](int t, int s) {
+#pragma unroll
+          for (int kb = 0; kb < D / 16; ++kb) {
+            const uint32_t off = (kb >> 2) * BLK_BYTES + (kb & 3) * 32;
+            umma_ss(tmem_base + t * 128, umma_smem_desc(sQ_u + t * TILE_BYTES + off, 16, 1024),
+                    umma_smem_desc(sK_u + s * TILE_BYTES + off, 16, 1024), idesc_qk, kb > 0 ? 1u : 0u);
+          }
+        };
+        auto issue_pv = [&](int t, int s, bool acc) {
+#pragma unroll
+          for (int kb = 0; kb < 8; ++kb) {
+            umma_ts(tmem_base + 256 + t * D, tmem_base + t * 128 + kb * 8,
+                    umma_smem_desc(sV_u + s * TILE_BYTES + kb * 2048, BLK_BYTES, 1024), idesc_pv,
+                    (acc || kb > 0) ? 1u : 0u);
+          }
+        };
+        mbar_wait(&q_full[0], 0);
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
+        issue_qk(0, 0);
+        tc_commit(&s_full[0]);
+        mbar_wait(&q_full[1], 0);
+        tc_fence_after();
+        issue_qk(1, 0);
+        tc_commit(&s_full[1]);
+        tc_commit(&k_empty[0]);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int s = j % NS;
+          const uint32_t ph = (j / NS) & 1;
+          const int s1 = (j + 1) % NS;
+          const uint32_t ph1 = ((j + 1) / NS) & 1;
+          const bool more = (j + 1 < n_tiles);
+          mbar_wait(&v_full[s], ph);
+          mbar_wait(&p_full[0], j & 1);
+          tc_fence_after();
+          issue_pv(0, s, j > 0);
+          tc_commit(&o_full[0]);
+          if (more) {
+            mbar_wait(&k_full[s1], ph1);
+            tc_fence_after();
+            issue_qk(0, s1);
+            tc_commit(&s_full[0]);
+          }
+          mbar_wait(&p_full[1], j & 1);
+          tc_fence_after();
+          issue_pv(1, s, j > 0);
+          tc_commit(&o_full[1]);
+          tc_commit(&v_empty[s]);
+          if (more) {
+            issue_qk(1, s1);
+            tc_commit(&s_full[1]);
+            tc_commit(&k_empty[s1]);
+          }
+        }
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- softmax warpgroups
+    setmaxnreg_inc<224>();
+    const int t = warp >> 2;
+    const int r = threadIdx.x & 127;
+    const int row = q0 + t * 128 + r;
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + t * 128;
+    const uint32_t tO = tmem_base + lane_off + 256 + t * D;
+    const int row_lim = CAUSAL ? min(a.Skv, row + a.causal_off + 1) : a.Skv;      // visible keys: [0,row_lim)
+    const int warp_row_lim = __shfl_sync(0xffffffffu, row_lim, 0);                // smallest in the warp
+    const bool has_aux = (a.mask.ptr != nullptr) || (a.bias.ptr != nullptr);
+    const int row_c = min(row, a.Sq - 1);
+    const uint8_t* mrow = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr) + b * a.mask.sb + h * a.mask.sh +
+                                           (long long)row_c * a.mask.sq
+                                     : nullptr;
+    const uint16_t* brow = a.bias.ptr ? reinterpret_cast<const uint16_t*>(a.bias.ptr) + b * a.bias.sb + h * a.bias.sh +
+                                            (long long)row_c * a.bias.sq
+                                      : nullptr;
+    const uint32_t bh_global = a.bh_offset + bh;
+
+    float m = (a.softmax_n > 0.f) ? 0.f : -INFINITY;   // running reference max (log2 domain)
+    float l = a.softmax_n;                             // running sum, starts at n (the virtual zero-logit key)
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int j0 = j * 128;
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      float s[128];
+      {
+        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+        tmem_ld_x32(tS + 0, sr + 0);
+        tmem_ld_x32(tS + 32, sr + 32);
+        tmem_ld_x32(tS + 64, sr + 64);
+        tmem_ld_x32(tS + 96, sr + 96);
+        tmem_wait_ld();
+      }
+#pragma unroll
+      for (int c = 0; c < 128; ++c) s[c] *= a.scale_log2;
+      if (has_aux) {
+#pragma unroll
+        for (int c = 0; c < 128; ++c) {
+          const int col = j0 + c;
+          if (col < a.Skv) {
+            if (brow) s[c] = fmaf(cvt16_to_f32<BF16>(brow[col]), kLog2e, s[c]);
+            if (mrow && mrow[col] == 0) s[c] = -INFINITY;
+          }
+        }
+      }
+      if (j0 + 128 > warp_row_lim) {
+        const int lim = row_lim - j0;
+#pragma unroll
+        for (int c = 0; c < 128; ++c) s[c] = (c < lim) ? s[c] : -INFINITY;
+      }
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int c = 4; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, s[c]); mx1 = fmaxf(mx1, s[c + 1]); mx2 = fmaxf(mx2, s[c + 2]); mx3 = fmaxf(mx3, s[c + 3]);
+      }
+      const float tmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      const bool upd = tmax > m + kRescaleThreshold;
+      float alpha = 1.f;
+      if (upd) {
+        alpha = ex2(m - tmax);
+        m = tmax;
+        l *= alpha;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, upd)) {
+        // rescale the O accumulator of this tile (rare): PV_{j-1} must have landed first
+        mbar_wait(&o_full[t], (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int cb = 0; cb < D / 32; ++cb) {
+          uint32_t o[32];
+          tmem_ld_x32(tO + cb * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x32(tO + cb * 32, o);
+        }
+      }
+      const float m_use = (m == -INFINITY) ? 0.f : m;
+      uint32_t kw[4];
+      if constexpr (DROPOUT) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) kw[i] = dropout_keep_word(a.key, bh_global, (uint32_t)row, (uint32_t)(j0 >> 5) + i, a.drop_thr);
+      }
+      uint32_t pr[64];
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 128; c += 4) {
+        float p0 = ex2(s[c] - m_use), p1 = ex2(s[c + 1] - m_use), p2 = ex2(s[c + 2] - m_use), p3 = ex2(s[c + 3] - m_use);
+        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+        if constexpr (DROPOUT) {
+          const uint32_t w = kw[c >> 5];
+          p0 = (w & (1u << ((c + 0) & 31))) ? p0 : 0.f;
+          p1 = (w & (1u << ((c + 1) & 31))) ? p1 : 0.f;
+          p2 = (w & (1u << ((c + 2) & 31))) ? p2 : 0.f;
+          p3 = (w & (1u << ((c + 3) & 31))) ? p3 : 0.f;
+        }
+        pr[c >> 1] = pack2<BF16>(p0, p1);
+        pr[(c >> 1) + 1] = pack2<BF16>(p2, p3);
+      }
+      l += (l0 + l1) + (l2 + l3);
+      tmem_st_x32(tS, pr);
+      tmem_st_x32(tS + 32, pr + 32);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+
+    // ------------------------------------------------------------------ epilogue
+    mbar_wait(&o_full[t], (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv = (l > 0.f) ? (DROPOUT ? a.inv_keep : 1.f) / l : 0.f;
+    uint8_t* sO = sQ + t * TILE_BYTES;    // Q_t is dead: every MMA that read it completed before o_full fired
+#pragma unroll
+    for (int cb = 0; cb < D / 32; ++cb) {
+      uint32_t o[32];
+      tmem_ld_x32(tO + cb * 32, o);
+      tmem_wait_ld();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {   // 4 x 16-byte chunks (8 elements each)
+        uint4 v;
+        v.x = pack2<BF16>(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+        v.y = pack2<BF16>(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+        v.z = pack2<BF16>(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+        v.w = pack2<BF16>(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+        const int col = cb * 32 + g * 8;
+        const int db = col >> 6;
+        const int cc = (col & 63) >> 3;
+        *reinterpret_cast<uint4*>(sO + db * BLK_BYTES + r * 128 + ((cc ^ (r & 7)) << 4)) = v;
+      }
+    }
+    if (row < a.Sq) a.lse[(long long)bh * a.Sq + row] = (l > 0.f) ? (m + log2f(l)) * kLn2 : INFINITY;
+    fence_proxy_async_smem();
+    named_bar_sync(1 + t, 128);
+    if (r == 0) {
+#pragma unroll
+      for (int db = 0; db < DB; ++db) tma_store_4d(&tm_o, sO + db * BLK_BYTES, db * 64, q0 + t * 128, h, b);
+      tma_store_commit();
+      tma_store_wait_all();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
+
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
+static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                                const FwdArgs& a, cudaStream_t stream) {
+  auto kern = fasn_fwd_kernel<D, BF16, CAUSAL, DROPOUT>;
+  constexpr int smem = FwdCfg<D>::SMEM_BYTES;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((a.Sq + 255) / 256, a.B * a.H, 1);
+  kern<<<grid, kFwdThreads, smem, stream>>>(tq, tk, tv, to, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fwd(int head_dim, bool bf16, bool causal, bool dropout, const CUtensorMap& tq, const CUtensorMap& tk,
+                       const CUtensorMap& tv, const CUtensorMap& to, const FwdArgs& a, cudaStream_t stream) {
+#define FASN_FWD_CASE(D_, BF_, C_, DR_) \
+  if (head_dim == D_ && bf16 == BF_ && causal == C_ && dropout == DR_) return launch_fwd_t<D_, BF_, C_, DR_>(tq, tk, tv, to, a, stream);
+  FASN_FWD_CASE(64, false, false, false) FASN_FWD_CASE(64, false, false, true)
+  FASN_FWD_CASE(64, false, true, false)  FASN_FWD_CASE(64, false, true, true)
+  FASN_FWD_CASE(64, true, false, false)  FASN_FWD_CASE(64, true, false, true)
+  FASN_FWD_CASE(64, true, true, false)   FASN_FWD_CASE(64, true, true, true)
+  FASN_FWD_CASE(128, false, false, false) FASN_FWD_CASE(128, false, false, true)
+  FASN_FWD_CASE(128, false, true, false)  FASN_FWD_CASE(128, false, true, true)
+  FASN_FWD_CASE(128, true, false, false)  FASN_FWD_CASE(128, true, false, true)
+  FASN_FWD_CASE(128, true, true, false)   FASN_FWD_CASE(128, true, true, true)
+#undef FASN_FWD_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace fasn

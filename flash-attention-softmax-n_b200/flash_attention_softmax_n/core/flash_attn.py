@@ -1,0 +1,212 @@
+"""`flash_attention_n`: the reference's 9-argument entry point
+(flash_attention_softmax_n/core/flash_attn.py:42-52) on hand-written sm_100a kernels.
+
+Same names, order, defaults and meaning of the arguments; what happens underneath differs:
+
+* the reference pads K/V with n zero rows and calls `scaled_dot_product_attention` (flash_attn.py:66-67,
+  115-124), which restricts n to integers and, on a B200, selects the math / mem-efficient backends with a
+  materialised (B,H,L,S+n) additive mask (flash_attn.py:28-33, 97-113).  Here the "+n" is the initial value
+  of the online-softmax running sum inside one fused kernel, n is any real >= 0, and causality is an index
+  comparison in registers;
+* there is no backend chooser (`_flash_attn_config`, flash_attn.py:17-35) and no fallback: inputs the
+  kernels do not cover raise `NotImplementedError` (use `slow_attention_n` for those).
+
+Covered: CUDA tensors, float16 / bfloat16, E == Ev in {64, 128}, 4-D query, 4-D or 3-D key/value
+(3-D = shared by all heads, flash_attn.py:75-79), any L and S, boolean `attn_mask` (True = attend),
+`attn_bias` of shape (H,L,S) or 4-D broadcastable, `is_causal` bottom-right aligned, dropout.
+Gradients flow to query, key and value (not to `attn_bias`).
+"""
+from __future__ import annotations
+
+import ctypes
+from math import sqrt
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from flash_attention_softmax_n import _native
+
+_SUPPORTED_HEAD_DIMS = (64, 128)
+
+
+def _next_philox(device: torch.device) -> Tuple[int, int]:
+    """(seed, offset) from torch's CUDA generator, advancing it so every call gets a fresh stream."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    seed = gen.initial_seed()
+    offset = gen.get_offset()
+    gen.set_offset(offset + 4)
+    return seed & 0xFFFFFFFFFFFFFFFF, offset // 4
+
+
+def _rowmajor(t: Tensor) -> Tensor:
+    """Kernels need unit stride on the last axis, 16-byte aligned rows and base pointer."""
+    if t.stride(-1) != 1 or any(s % 8 for s in t.stride()[:-1]) or t.data_ptr() % 16:
+        t = t.contiguous()
+    return t
+
+
+def _canon_aux(t: Tensor, S: int) -> Tensor:
+    """Mask / bias layout the kernels read: unit stride along keys; batch, head and query axes may be
+    broadcast (size 1 or stride 0), which the C ABI expresses as a zero stride."""
+    if t.size(-1) != S:                       # size-1 key axis: give it its real extent
+        t = t.expand(*t.shape[:-1], S)
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _prepare_aux(attn_mask: Optional[Tensor], attn_bias: Optional[Tensor], q: Tensor, S: int
+                 ) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    B, H, L, _ = q.shape
+    if attn_mask is not None:
+        assert attn_mask.ndim == 4                                           # flash_attn.py:88
+        if attn_mask.dtype != torch.bool:
+            raise TypeError("attn_mask must be a boolean tensor (True = take part in attention)")
+        attn_mask.expand(B, H, L, S)                                         # shape check only (flash_attn.py:89)
+        attn_mask = _canon_aux(attn_mask, S)
+    if attn_bias is not None:
+        if attn_bias.requires_grad:
+            raise NotImplementedError("gradients with respect to attn_bias are not implemented by the fused kernel")
+        if attn_bias.ndim == 3:
+            attn_bias = attn_bias.unsqueeze(0)                               # 'h i j -> 1 h i j' (flash_attn.py:101-102)
+        assert attn_bias.ndim == 4
+        attn_bias.expand(B, H, L, S)                                         # shape check (flash_attn.py:103)
+        attn_bias = _canon_aux(attn_bias.to(q.dtype), S)
+    return attn_mask, attn_bias
+
+
+def _fill_common(p: _native.FasnParams, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, heads_kv: int,
+                 n: float, scale: float, causal: bool, dropout_p: float, seed: int, offset: int, bh_offset: int,
+                 mask: Optional[Tensor], bias: Optional[Tensor]) -> None:
+    B, H, L, D = q.shape
+    p.struct_size = ctypes.sizeof(_native.FasnParams)
+    p.dtype = _native.dtype_code(q.dtype)
+    p.batch, p.heads, p.heads_kv = B, H, heads_kv
+    p.seqlen_q, p.seqlen_kv, p.head_dim = L, k.shape[2], D
+    p.q, p.k, p.v, p.o = (_native.tensor_view(t) for t in (q, k, v, o))
+    p.lse = lse.data_ptr()
+    p.softmax_n, p.scale, p.is_causal, p.dropout_p = float(n), float(scale), int(bool(causal)), float(dropout_p)
+    p.philox_seed, p.philox_offset, p.bh_offset = seed, offset, bh_offset
+    p.mask, p.bias = _native.aux_view(mask), _native.aux_view(bias)
+    p.stream = _native.current_stream_ptr(q.device)
+
+
+class _FusedAttentionN(torch.autograd.Function):
+    """Counterpart of the reference's `_FlashAttentionN` (flash_attn_triton.py:241-336): saves
+    (q, k, v, o, lse) and returns gradients for q, k, v only."""
+
+    @staticmethod
+    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, heads_kv: int, n: float, scale: float, causal: bool,
+                dropout_p: float, mask: Optional[Tensor], bias: Optional[Tensor], seed: int, offset: int,
+                bh_offset: int) -> Tensor:
+        lib = _native.load()
+        B, H, L, D = q.shape
+        with torch.cuda.device(q.device):
+            o = torch.empty((B, H, L, D), dtype=q.dtype, device=q.device)     # fresh outputs (flash_attn_triton.py:271)
+            lse = torch.empty((B, H, L), dtype=torch.float32, device=q.device)
+            p = _native.FasnParams()
+            _fill_common(p, q, k, v, o, lse, heads_kv, n, scale, causal, dropout_p, seed, offset, bh_offset, mask, bias)
+            _native.check(lib.fasn_fwd(ctypes.byref(p)), "fasn_fwd")
+        ctx.save_for_backward(q, k, v, o, lse, mask, bias)
+        ctx.cfg = (heads_kv, n, scale, causal, dropout_p, seed, offset, bh_offset)
+        return o
+
+    @staticmethod
+    def backward(ctx, do: Tensor):
+        q, k, v, o, lse, mask, bias = ctx.saved_tensors
+        heads_kv, n, scale, causal, dropout_p, seed, offset, bh_offset = ctx.cfg
+        lib = _native.load()
+        B, H, L, D = q.shape
+        S = k.shape[2]
+        do = _rowmajor(do)
+        Lp = (L + 127) // 128 * 128
+        with torch.cuda.device(q.device):
+            dq = torch.empty((B, H, L, D), dtype=q.dtype, device=q.device)
+            # dK / dV are produced per query head; shared K/V (heads_kv == 1) are reduced over heads below
+            dk = torch.empty((B, H, S, D), dtype=q.dtype, device=q.device)
+            dv = torch.empty((B, H, S, D), dtype=q.dtype, device=q.device)
+            ws = torch.empty((2, B, H, Lp), dtype=torch.float32, device=q.device)
+            dq_accum = torch.empty((B, H, Lp, D), dtype=torch.float32, device=q.device)
+            p = _native.FasnParams()
+            _fill_common(p, q, k, v, o, lse, heads_kv, n, scale, causal, dropout_p, seed, offset, bh_offset, mask, bias)
+            p.dout, p.dq, p.dk, p.dv = (_native.tensor_view(t) for t in (do, dq, dk, dv))
+            p.delta, p.dq_accum = ws.data_ptr(), dq_accum.data_ptr()
+            _native.check(lib.fasn_bwd(ctypes.byref(p)), "fasn_bwd")
+        if heads_kv == 1 and H > 1:
+            dk = dk.sum(dim=1, keepdim=True, dtype=torch.float32).to(q.dtype)
+            dv = dv.sum(dim=1, keepdim=True, dtype=torch.float32).to(q.dtype)
+        return dq, dk, dv, None, None, None, None, None, None, None, None, None, None
+
+
+def flash_attention_n(
+        query: Tensor,
+        key: Tensor,
+        value: Tensor,
+        softmax_n_param: Optional[float] = None,
+        scale: Optional[float] = None,
+        dropout_p: float = 0.,
+        attn_mask: Optional[Tensor] = None,
+        attn_bias: Optional[Tensor] = None,
+        is_causal: bool = False,
+        *,
+        _philox: Optional[Tuple[int, int]] = None,
+        _bh_offset: int = 0,
+) -> Tensor:
+    """
+    Fused attention with softmax_n on B200.
+
+    :param query: Query tensor; shape (N, H, L, E).
+    :param key: Key tensor; shape (N, H, S, E) or (N, S, E) (shared by all heads).
+    :param value: Value tensor; shape (N, H, S, Ev) or (N, S, Ev); Ev == E.
+    :param softmax_n_param: Regularization parameter n >= 0 of softmax_n (any real number; None = 0).
+    :param scale: Scaling factor applied prior to softmax. If None, the default value is set to 1 / sqrt(E).
+    :param dropout_p: Dropout probability; if greater than 0.0, dropout is applied.
+    :param attn_mask: Boolean attention mask, 4-D, broadcastable to (N, H, L, S); True = attend.
+    :param attn_bias: Additive (e.g. ALiBi) bias; shape (H, L, S) or 4-D broadcastable to (N, H, L, S).
+    :param is_causal: If true, causal masking aligned to the bottom-right corner (row i sees j <= i + S - L).
+    :return: Attention output; shape (N, H, L, Ev).
+
+    `_philox` (seed, offset) pins the dropout stream and `_bh_offset` is the global index of the first
+    (batch, head) unit of this call; both exist for tests and for batch x head sharding (parallel.py).
+    """
+    n = 0.0 if softmax_n_param is None else float(softmax_n_param)
+    if n < 0:
+        raise ValueError("softmax_n_param must be >= 0")
+    if query.ndim != 4:
+        raise ValueError(f"query must be 4-D (N, H, L, E), got {tuple(query.shape)}")        # flash_attn.py:85
+    if not query.is_cuda:
+        raise NotImplementedError("flash_attention_n runs on CUDA (B200) tensors only; there is no CPU path. "
+                                  "Use slow_attention_n for eager evaluation.")
+    if query.dtype not in (torch.float16, torch.bfloat16) or key.dtype != query.dtype or value.dtype != query.dtype:
+        raise NotImplementedError(f"fused kernel supports float16/bfloat16 with matching dtypes, got "
+                                  f"{query.dtype}/{key.dtype}/{value.dtype}; use slow_attention_n")
+    B, H, L, E = query.shape
+    heads_kv = H
+    if key.ndim == 3:                                                     # 'b ... -> b 1 ...' (flash_attn.py:75-76)
+        key = key.unsqueeze(1)
+    if value.ndim == 3:
+        value = value.unsqueeze(1)
+    if key.ndim != 4 or value.ndim != 4:
+        raise ValueError("key and value must be 3-D or 4-D")
+    if key.shape[1] != value.shape[1] or key.shape[1] not in (1, H):
+        raise ValueError(f"key/value heads {key.shape[1]}/{value.shape[1]} must both be {H} or 1")
+    if key.shape[1] == 1 and H > 1:
+        heads_kv = 1
+    S = key.shape[2]
+    if key.shape[0] != B or value.shape[0] != B or value.shape[2] != S or key.shape[3] != E:
+        raise ValueError("inconsistent query/key/value shapes")
+    if value.shape[3] != E or E not in _SUPPORTED_HEAD_DIMS:
+        raise NotImplementedError(f"fused kernel supports E == Ev in {_SUPPORTED_HEAD_DIMS}, got E={E}, "
+                                  f"Ev={value.shape[3]}; use slow_attention_n")
+    if not 0.0 <= dropout_p < 1.0:
+        raise ValueError("dropout_p must be in [0, 1)")
+    sm_scale = 1.0 / sqrt(E) if scale is None else float(scale)           # flash_attn.py:59, 81-83
+
+    query, key, value = _rowmajor(query), _rowmajor(key), _rowmajor(value)
+    mask, bias = _prepare_aux(attn_mask, attn_bias, query, S)
+    seed, offset = (0, 0)
+    if dropout_p > 0.0:
+        seed, offset = _philox if _philox is not None else _next_philox(query.device)
+    return _FusedAttentionN.apply(query, key, value, heads_kv, n, sm_scale, bool(is_causal), float(dropout_p),
+                                  mask, bias, int(seed), int(offset), int(_bh_offset))

@@ -1,0 +1,114 @@
+"""Batch x head sharding of attention over the GPUs of one node (one process per GPU, torch.distributed).
+
+The reference has no distributed code; this is the single data-parallel step the
+north star asks for.  Every (batch, head) pair is an independent attention problem (the reference's grid axis
+`off_hz`, flash_attn_triton.py:46,274), so the flattened unit axis is cut into contiguous slabs, one per
+rank, with NO collective on the data path of the kernels.  Two ways to use it:
+
+* resident slabs (data-parallel training: each rank already owns its units): call `local_attention`;
+* root-held tensors: `sharded_attention` scatters contiguous slabs of Q/K/V from the root with point-to-point
+  sends (NCCL over NVLink/NVSwitch), runs the local kernel, and gathers O back.
+
+Dropout masks are keyed by the GLOBAL unit index, so results do not depend on the world size.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def partition_units(n_units: int, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous, near-equal [start, stop) slabs of the flattened (batch, head) axis; the first
+    `n_units % world_size` ranks get one extra unit."""
+    if n_units < 0 or world_size <= 0:
+        raise ValueError("n_units must be >= 0 and world_size > 0")
+    base, extra = divmod(n_units, world_size)
+    out, start = [], 0
+    for r in range(world_size):
+        stop = start + base + (1 if r < extra else 0)
+        out.append((start, stop))
+        start = stop
+    return out
+
+
+def scatter_units(full: Optional[Tensor], unit_shape: Tuple[int, ...], dtype: torch.dtype, device: torch.device,
+                  n_units: int, root: int = 0, group=None) -> Tensor:
+    """Root holds `full` of shape (n_units, *unit_shape) (contiguous); every rank returns its slab."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    parts = partition_units(n_units, world)
+    lo, hi = parts[rank]
+    if rank == root:
+        assert full is not None and full.shape[0] == n_units and full.is_contiguous()
+        reqs = []
+        for r, (a, b) in enumerate(parts):
+            if r != root and b > a:
+                reqs.append(dist.isend(full[a:b], dst=dist.get_global_rank(group, r) if group else r, group=group))
+        local = full[lo:hi].clone()
+        for q in reqs:
+            q.wait()
+        return local
+    local = torch.empty((hi - lo, *unit_shape), dtype=dtype, device=device)
+    if hi > lo:
+        dist.recv(local, src=dist.get_global_rank(group, root) if group else root, group=group)
+    return local
+
+
+def gather_units(local: Tensor, n_units: int, root: int = 0, group=None) -> Optional[Tensor]:
+    """Inverse of `scatter_units`: the root returns (n_units, *unit_shape), other ranks None."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    parts = partition_units(n_units, world)
+    lo, hi = parts[rank]
+    assert local.shape[0] == hi - lo
+    if rank == root:
+        full = torch.empty((n_units, *local.shape[1:]), dtype=local.dtype, device=local.device)
+        reqs = []
+        for r, (a, b) in enumerate(parts):
+            if r != root and b > a:
+                reqs.append(dist.irecv(full[a:b], src=dist.get_global_rank(group, r) if group else r, group=group))
+        full[lo:hi].copy_(local)
+        for q in reqs:
+            q.wait()
+        return full
+    if hi > lo:
+        dist.send(local.contiguous(), dst=dist.get_global_rank(group, root) if group else root, group=group)
+    return None
+
+
+def local_attention(q_units: Tensor, k_units: Tensor, v_units: Tensor, unit_offset: int, *,
+                    attn_fn: Optional[Callable] = None, **kwargs) -> Tensor:
+    """Attention over a resident slab.  `*_units` are (U, S, D): U independent (batch, head) units whose
+    global indices start at `unit_offset`.  Returns (U, L, D)."""
+    if attn_fn is None:
+        from flash_attention_softmax_n.core.flash_attn import flash_attention_n as attn_fn
+        kwargs = dict(kwargs, _bh_offset=unit_offset)
+    if q_units.shape[0] == 0:
+        return q_units.new_empty(q_units.shape)
+    out = attn_fn(q_units.unsqueeze(0), k_units.unsqueeze(0), v_units.unsqueeze(0), **kwargs)
+    return out.squeeze(0)
+
+
+def sharded_attention(query: Optional[Tensor], key: Optional[Tensor], value: Optional[Tensor], *,
+                      shape: Tuple[int, int, int, int, int], dtype: torch.dtype, device: torch.device,
+                      root: int = 0, group=None, attn_fn: Optional[Callable] = None, **kwargs) -> Optional[Tensor]:
+    """Scatter (B,H,L,D)/(B,H,S,D) tensors held by `root` over the group by (batch, head) slabs, run attention
+    on every rank, gather O on the root.  `shape` = (B, H, L, S, D) must be passed on every rank.
+    Returns (B,H,L,D) on the root and None elsewhere.  attn_mask / attn_bias are not sharded here."""
+    if "attn_mask" in kwargs or "attn_bias" in kwargs:
+        raise NotImplementedError("sharded_attention does not distribute attn_mask / attn_bias")
+    B, H, L, S, D = shape
+    n_units = B * H
+    rank = dist.get_rank(group)
+    on_root = rank == root
+    qf = query.reshape(n_units, L, D).contiguous() if on_root else None
+    kf = key.reshape(n_units, S, D).contiguous() if on_root else None
+    vf = value.reshape(n_units, S, D).contiguous() if on_root else None
+    ql = scatter_units(qf, (L, D), dtype, device, n_units, root, group)
+    kl = scatter_units(kf, (S, D), dtype, device, n_units, root, group)
+    vl = scatter_units(vf, (S, D), dtype, device, n_units, root, group)
+    lo, _ = partition_units(n_units, dist.get_world_size(group))[rank]
+    ol = local_attention(ql, kl, vl, lo, attn_fn=attn_fn, **kwargs)
+    full = gather_units(ol.contiguous(), n_units, root, group)
+    return full.reshape(B, H, L, D) if on_root else None

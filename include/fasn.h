@@ -1,0 +1,134 @@
+/* fasn.h -- C ABI of libfasn.so: fused attention with softmax_n for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for ONE hot path of softmax1/Flash-Attention-Softmax-N (reference paths are
+ * relative to the reference repository root):
+ *
+ *   fasn_fwd  replaces  flash_attention_n(query, key, value, softmax_n_param, scale, dropout_p, attn_mask,
+ *                       attn_bias, is_causal)           flash_attention_softmax_n/core/flash_attn.py:42-124
+ *             and       _FlashAttentionN.forward        flash_attention_softmax_n/core/flash_attn_triton.py:243-299
+ *                       (_fwd_kernel                    flash_attention_softmax_n/core/flash_attn_triton.py:30-126)
+ *   fasn_bwd  replaces  _FlashAttentionN.backward       flash_attention_softmax_n/core/flash_attn_triton.py:301-336
+ *                       (_bwd_preprocess :129-143, _bwd_kernel :146-235) and the aten autograd of the SDPA call
+ *                       at flash_attn.py:115-124.
+ *
+ * The reference has no native code, so there is no existing FFI to mirror: these entry points are what a
+ * ctypes/cffi binding inside flash_attention_softmax_n/core/flash_attn.py binds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers unless the name says host;
+ *   - tensors are (B, H, S, D) with arbitrary element strides for B, H, S and unit stride for D;
+ *     strides are in ELEMENTS; base pointers and byte strides must be multiples of 16 bytes;
+ *   - every function returns 0 on success, a negative FASN_E* code for a rejected argument, or a positive
+ *     cudaError_t; fasn_last_error() returns a thread-local description of the last failure;
+ *   - launches are asynchronous on `stream`; nothing here synchronises the device;
+ *   - re-entrant; the only global state is an immutable driver entry point looked up once.
+ */
+#ifndef FASN_H_
+#define FASN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FASN_ABI_VERSION 1
+
+enum { FASN_FP16 = 0, FASN_BF16 = 1 };
+
+enum {
+  FASN_EINVAL = -1,      /* null pointer, bad size, bad struct_size                       */
+  FASN_EUNSUPPORTED = -2,/* head dim / dtype / alignment outside what the kernels handle   */
+  FASN_EDRIVER = -3      /* cuTensorMapEncodeTiled unavailable or failed                   */
+};
+
+/* One (B, H, S, D) tensor view. */
+typedef struct FasnTensor {
+  void*   ptr;        /* device pointer to element (0,0,0,0)                                            */
+  int64_t stride_b;   /* element stride between batches                                                 */
+  int64_t stride_h;   /* element stride between heads (ignored for K/V when heads_kv == 1)              */
+  int64_t stride_s;   /* element stride between sequence positions (>= D)                               */
+} FasnTensor;
+
+/* Optional dense mask / bias views, element (b,h,i,j) at ptr[b*stride_b + h*stride_h + i*stride_q + j];
+ * a stride of 0 broadcasts that axis (flash_attn.py:88-89 expands the mask, :100-103 the bias). */
+typedef struct FasnAux {
+  const void* ptr;    /* NULL = absent                                                                  */
+  int64_t stride_b, stride_h, stride_q;
+} FasnAux;
+
+typedef struct FasnParams {
+  uint32_t struct_size;   /* sizeof(FasnParams), checked                                               */
+  uint32_t dtype;         /* FASN_FP16 | FASN_BF16 : element type of q,k,v,o,dout,dq,dk,dv and bias     */
+  int32_t  batch;         /* B                                                                          */
+  int32_t  heads;         /* H  (query heads)                                                           */
+  int32_t  heads_kv;      /* H, or 1 when K/V are shared by all heads (3-D key/value, flash_attn.py:75-79) */
+  int32_t  seqlen_q;      /* L                                                                          */
+  int32_t  seqlen_kv;     /* S                                                                          */
+  int32_t  head_dim;      /* E == Ev, 64 or 128                                                         */
+
+  FasnTensor q, k, v;     /* inputs                                                                     */
+  FasnTensor o;           /* fwd: output (B,H,L,D);  bwd: the forward's output (input)                  */
+  float*     lse;         /* (B,H,L) fp32 contiguous: ln(n + sum_j exp s_ij).  fwd writes, bwd reads    */
+
+  /* backward only */
+  FasnTensor dout;        /* dL/dO                                                                      */
+  FasnTensor dq, dk, dv;  /* outputs; dk, dv are per QUERY head (B,H,S,D) even when heads_kv == 1       */
+  float*     delta;       /* workspace 2 x (B,H,Lp) fp32 (delta, then LSE*log2e), Lp = L rounded up to 128 */
+  float*     dq_accum;    /* workspace (B,H,Lp,D) fp32; fasn_bwd zero-fills it itself                   */
+
+  float    softmax_n;     /* n >= 0 (real valued: superset of the reference's integer zero-pad trick)   */
+  float    scale;         /* logit scale; the caller resolves the 1/sqrt(E) default (flash_attn.py:59)  */
+  int32_t  is_causal;     /* bottom-right aligned: row i sees keys j <= i + (S - L) (flash_attn.py:38-39) */
+  float    dropout_p;     /* in [0,1); kept probabilities are scaled by 1/(1-p)                         */
+  uint64_t philox_seed;   /* dropout stream; the keep mask is a pure function of                        */
+  uint64_t philox_offset; /*   (seed, offset, bh_offset + b*H + h, i, j)                                */
+  int64_t  bh_offset;     /* global index of this call's first (batch, head) unit (multi-GPU sharding)  */
+
+  FasnAux  mask;          /* uint8/bool, nonzero = attend (flash_attn.py:61,70)                         */
+  FasnAux  bias;          /* same dtype as q; added after scaling (flash_attn.py:81-83,100-113)         */
+
+  void*    stream;        /* cudaStream_t                                                               */
+} FasnParams;
+
+/* ABI version of the loaded library (== FASN_ABI_VERSION it was built with). */
+int fasn_version(void);
+
+/* Thread-local description of the most recent failure on the calling thread ("" if none). */
+const char* fasn_last_error(void);
+
+/* O = dropout(softmax_n(scale Q K^T + bias, masked)) V ; also writes lse. */
+int fasn_fwd(const FasnParams* p);
+
+/* dQ, dK, dV from (Q, K, V, O, dO, lse); regenerates the forward's dropout mask from the philox fields. */
+int fasn_bwd(const FasnParams* p);
+
+/* Bytes the caller must provide for FasnParams.delta and FasnParams.dq_accum. */
+int fasn_bwd_workspace(const FasnParams* p, uint64_t* delta_bytes, uint64_t* dq_accum_bytes);
+
+/* Test hook: write the dropout keep mask the kernels use, as (B,H,L,S) uint8 (1 = keep), to `out`. */
+int fasn_dropout_mask(uint8_t* out, int32_t batch, int32_t heads, int32_t seqlen_q, int32_t seqlen_kv,
+                      float dropout_p, uint64_t philox_seed, uint64_t philox_offset, int64_t bh_offset,
+                      void* stream);
+
+/* Bring-up hook: one 128x128x128 tcgen05 MMA through the same descriptor builders the kernels use.
+ *   mode 0: C = X * Y^T  (A, B K-major in shared memory)         -- the Q K^T form
+ *   mode 1: C = X * Y    (A from tensor memory, B MN-major)      -- the P V form
+ *   mode 2: C = X^T * Y  (A, B MN-major in shared memory)        -- the dQ = dS K form
+ *   mode 3: C = X * Y    (A K-major, B MN-major in shared memory)-- the dK = dS^T Q form
+ * x, y: 128x128 row-major 16-bit device arrays; c: 128x128 row-major fp32. */
+int fasn_probe(int mode, uint32_t dtype, const void* x, const void* y, float* c, void* stream);
+
+/* Host-buffer convenience used for end-to-end measurement: copies q,k,v (and dout) from HOST memory,
+ * runs fwd (+bwd when dout_host != NULL) and copies o (and dq,dk,dv) back.  Contiguous (B,H,S,D) layouts.
+ * Uses an internal device arena sized on first use; synchronises `stream` before returning. */
+int fasn_attention_host(uint32_t dtype, int32_t batch, int32_t heads, int32_t seqlen_q, int32_t seqlen_kv,
+                        int32_t head_dim, const void* q_host, const void* k_host, const void* v_host,
+                        void* o_host, const void* dout_host, void* dq_host, void* dk_host, void* dv_host,
+                        float softmax_n, float scale, int32_t is_causal, float dropout_p,
+                        uint64_t philox_seed, uint64_t philox_offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASN_H_ */

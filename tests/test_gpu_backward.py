@@ -1,0 +1,97 @@
+"""Backward parity (dQ, dK, dV through autograd -> fasn_bwd) against the float64 oracle."""
+import pytest
+import torch
+
+from oracle import attention_oracle as orc
+from tests._util import make_qkv, oracle_all, native_lowp_all, check_close, run_fused, REL_L2
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # B  H  L     S     D    n     causal scale
+    (1, 1, 128, 128, 64, 1.0, False, None),
+    (2, 2, 256, 256, 128, 0.5, True, None),
+    (1, 2, 384, 256, 64, 0.0, False, 0.1),
+    (1, 2, 200, 333, 128, 4.0, False, 0.5),      # ragged
+    (1, 2, 333, 200, 64, 1.0, True, None),       # S < L causal: some K/V tiles see few queries, some rows see no key
+    (2, 1, 96, 160, 64, 0.5, True, None),        # S > L causal
+    (1, 1, 640, 640, 128, 1e-3, True, None),
+    (6, 1, 1024, 1024, 64, 1.0, True, 0.5),      # the reference's GPU test shape (tests/gpu/core/test_flash_attn.py:16-18)
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,H,L,S,D,n,causal,scale", CASES)
+def test_backward_matches_oracle(fasn_lib, B, H, L, S, D, n, causal, scale, dtype):
+    q, k, v, do = make_qkv(B, H, L, S, D, dtype, seed=3 * L + S)
+    kw = dict(softmax_n_param=n, scale=scale, is_causal=causal)
+    got = run_fused(q, k, v, do, **kw)
+    want = oracle_all(q, k, v, do, **kw)
+    native = native_lowp_all(q, k, v, do, **kw)
+    for name, g, w, nat in zip(("O", "dQ", "dK", "dV"), got, want, native):
+        assert g.shape == w.shape and g.dtype == dtype
+        check_close(name, g, w, nat, dtype, rel_scale=1.5)
+
+
+@pytest.mark.parametrize("name", ["c1", "causal", "n0c"])
+def test_backward_golden_vectors(fasn_lib, golden, name):
+    n, scale, causal = golden[f"slow_{name}_meta"]
+    dtype = torch.bfloat16
+    q, k, v, do = (torch.from_numpy(golden[f"slow_{name}_{x}"]).to(dtype).cuda() for x in ("q", "k", "v", "do"))
+    got = run_fused(q, k, v, do, softmax_n_param=float(n), scale=None if scale < 0 else float(scale), is_causal=bool(causal))
+    for key, g in zip(("o", "dq", "dk", "dv"), got):
+        want = torch.from_numpy(golden[f"slow_{name}_{key}"]).double()
+        assert orc.rel_l2(g, want) <= 1.5 * REL_L2[dtype], key
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("causal", [False, True])
+def test_backward_dropout_same_mask(fasn_lib, dtype, causal):
+    """The backward kernel regenerates the forward's keep mask from (seed, offset): gradients must equal the
+    oracle's with that exact mask."""
+    B, H, L, S, D, p = 1, 2, 300, 260, 128, 0.1
+    q, k, v, do = make_qkv(B, H, L, S, D, dtype, seed=77)
+    seed, offset = 0x5EED, 0
+    keep = orc.dropout_keep_mask(seed, offset, B, H, L, S, p)
+    kw = dict(softmax_n_param=0.5, is_causal=causal)
+    got = run_fused(q, k, v, do, dropout_p=p, _philox=(seed, offset), **kw)
+    want = oracle_all(q, k, v, do, keep_mask=keep, dropout_p=p, **kw)
+    for name, g, w in zip(("O", "dQ", "dK", "dV"), got, want):
+        check_close(name + "(dropout)", g, w, None, dtype, rel_scale=2.0)
+
+
+def test_backward_mask_bias_and_shared_kv(fasn_lib):
+    dtype = torch.bfloat16
+    B, H, L, S, D = 2, 3, 136, 200, 64
+    q, k, v, do = make_qkv(B, H, L, S, D, dtype, seed=13)
+    g = torch.Generator().manual_seed(4)
+    mask = torch.rand(B, 1, L, S, generator=g) > 0.3
+    mask[..., 0] = True
+    bias = torch.randn(H, L, S, generator=g).to(dtype)
+    kw = dict(softmax_n_param=2, scale=0.2, is_causal=True)
+    got = run_fused(q, k, v, do, attn_mask=mask.cuda(), attn_bias=bias.cuda(), **kw)
+    want = oracle_all(q, k, v, do, attn_mask=mask, attn_bias=bias.double(), **kw)
+    for name, a, b in zip(("O", "dQ", "dK", "dV"), got, want):
+        check_close(name + "(mask,bias)", a, b, None, dtype, rel_scale=1.5)
+    # shared K/V: gradients are summed over the heads
+    q, k, v, do = make_qkv(2, 4, 130, 190, 64, dtype, seed=9, heads_kv=1)
+    got = run_fused(q, k[:, 0], v[:, 0], do, softmax_n_param=1)
+    want = oracle_all(q, k[:, 0], v[:, 0], do, softmax_n_param=1)
+    for name, a, b in zip(("O", "dQ", "dK", "dV"), got, want):
+        assert a.shape == b.shape
+        check_close(name + "(shared kv)", a, b, None, dtype, rel_scale=2.0)
+
+
+def test_triton_alias_forward_backward(fasn_lib):
+    """flash_attention_n_triton(query, key, value, is_causal, scale, softmax_n_param): the reference's Triton test
+    shape family (tests/gpu/core/test_flash_attn_triton.py:13-48), real-valued n, gradients included."""
+    from flash_attention_softmax_n import flash_attention_n_triton
+    dtype = torch.float16
+    q, k, v, do = make_qkv(2, 4, 512, 512, 64, dtype, seed=31)
+    for n, causal in [(1e-3, True), (3.0, False), (0.5, True)]:
+        qq, kk, vv = (t.detach().clone().requires_grad_() for t in (q, k, v))
+        o = flash_attention_n_triton(qq, kk, vv, causal, 0.2, n)
+        o.backward(do)
+        want = oracle_all(q, k, v, do, softmax_n_param=n, scale=0.2, is_causal=causal)
+        for name, a, b in zip(("O", "dQ", "dK", "dV"), (o, qq.grad, kk.grad, vv.grad), want):
+            check_close(name + "(triton alias)", a, b, None, dtype, rel_scale=1.5)

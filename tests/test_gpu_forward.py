@@ -1,0 +1,140 @@
+"""Forward parity of the fused sm_100a kernel (through flash_attention_n -> ctypes -> fasn_fwd) against the oracle."""
+import math
+
+import pytest
+import torch
+
+from oracle import attention_oracle as orc
+from tests._util import make_qkv, oracle_all, native_lowp_all, check_close, REL_L2
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # B  H  L     S     D    n     causal scale
+    (1, 1, 128, 128, 64, 1.0, False, None),      # BASELINE.json configs[0] shape
+    (2, 3, 256, 256, 128, 0.5, True, None),
+    (2, 2, 384, 384, 64, 0.0, False, 0.1),
+    (1, 2, 200, 333, 128, 4.0, False, 0.5),      # ragged L and S
+    (1, 2, 333, 200, 64, 1.0, True, None),       # causal with S < L: leading rows see no key
+    (2, 1, 96, 160, 64, 0.5, True, None),        # causal with S > L (bottom-right aligned)
+    (1, 1, 1, 77, 128, 1.0, False, None),        # single query row
+    (1, 2, 1024, 1152, 64, 1e-3, True, 0.3),     # the reference's GPU analytic-test shape
+    (1, 1, 640, 640, 128, 1e-6, True, None),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,H,L,S,D,n,causal,scale", CASES)
+def test_forward_matches_oracle(fasn_lib, B, H, L, S, D, n, causal, scale, dtype):
+    from flash_attention_softmax_n import flash_attention_n
+    q, k, v, do = make_qkv(B, H, L, S, D, dtype, seed=L + S)
+    kw = dict(softmax_n_param=n, scale=scale, is_causal=causal)
+    out = flash_attention_n(q, k, v, **kw)
+    torch.cuda.synchronize()
+    assert out.shape == (B, H, L, D) and out.dtype == dtype
+    want = orc.slow_attention_n(q.double().cpu(), k.double().cpu(), v.double().cpu(), **kw)
+    native = orc.slow_attention_n(q, k, v, **kw)
+    check_close("O", out, want, native, dtype)
+
+
+@pytest.mark.parametrize("name", ["c1", "causal", "n0c"])
+def test_forward_golden_vectors(fasn_lib, golden, name):
+    """Inputs and outputs produced by the reference's own slow_attention_n (tests/golden/make_golden.py);
+    the inputs are exactly representable in bf16, so the kernel sees the very same numbers."""
+    from flash_attention_softmax_n import flash_attention_n
+    n, scale, causal = golden[f"slow_{name}_meta"]
+    for dtype in (torch.bfloat16, torch.float16):
+        q, k, v = (torch.from_numpy(golden[f"slow_{name}_{x}"]).to(dtype).cuda() for x in "qkv")
+        out = flash_attention_n(q, k, v, softmax_n_param=float(n), scale=None if scale < 0 else float(scale),
+                                is_causal=bool(causal))
+        want = torch.from_numpy(golden[f"slow_{name}_o"]).double()
+        assert orc.rel_l2(out, want) <= REL_L2[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n", [0, 1, 4])
+@pytest.mark.parametrize("weight", [10, 3, 0.5, 0.04, 0, -0.02, -0.5, -3, -10])
+def test_forward_analytic(fasn_lib, n, weight, dtype):
+    """The reference's closed-form GPU test (tests/gpu/core/test_flash_attn.py:51-91): constant inputs,
+    L=1024, S=1152, E=Ev=64, scale 0.3; same tolerances (atol 1e-3; causal rtol 2e-3, bf16 2e-2)."""
+    from flash_attention_softmax_n import flash_attention_n
+    N, L, S, E, scale = 6, 1024, 1152, 64, 0.3
+    q = torch.full((N, 1, L, E), weight, dtype=dtype, device="cuda")
+    k = torch.full((N, 1, S, E), weight, dtype=dtype, device="cuda")
+    v = torch.full((N, 1, S, E), weight, dtype=dtype, device="cuda")
+    w = q[0, 0, 0, 0].item()                         # the value after rounding to the 16-bit type
+    out = flash_attention_n(q, k, v, scale=scale, softmax_n_param=n)
+    expect = orc.analytic_answer(N, L, S, E, E, scale, w, n)
+    torch.testing.assert_close(out[:, 0].double().cpu(), expect, atol=1e-3 * max(1.0, abs(w)), rtol=4e-3 if dtype == torch.bfloat16 else 5e-4)
+    outc = flash_attention_n(q, k, v, scale=scale, is_causal=True, softmax_n_param=n)
+    expect_c = orc.analytic_causal_answer(N, L, S, E, E, scale, w, n)
+    torch.testing.assert_close(outc.double().sum(dim=0).sum(dim=-1)[0].cpu(), expect_c, atol=1e-6,
+                               rtol=2e-2 if dtype == torch.bfloat16 else 2e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_forward_mask_and_bias(fasn_lib, dtype):
+    """attn_mask (bool, broadcast over heads) AND causal, plus a 3-D (H,L,S) bias: semantics of flash_attn.py:87-113."""
+    from flash_attention_softmax_n import flash_attention_n
+    B, H, L, S, D = 2, 3, 200, 264, 64
+    q, k, v, _ = make_qkv(B, H, L, S, D, dtype, seed=5)
+    g = torch.Generator().manual_seed(11)
+    mask = (torch.rand(B, 1, L, S, generator=g) > 0.3)
+    mask[..., 0] = True
+    mask[0, 0, 7, :] = False                       # one fully masked row: result must be exactly 0
+    bias = torch.randn(H, L, S, generator=g).to(dtype)
+    kw = dict(softmax_n_param=2, scale=0.2, is_causal=True)
+    out = flash_attention_n(q, k, v, attn_mask=mask.cuda(), attn_bias=bias.cuda(), **kw)
+    want = orc.slow_attention_n(q.double().cpu(), k.double().cpu(), v.double().cpu(), attn_mask=mask,
+                                attn_bias=bias.double(), **kw)
+    native = orc.slow_attention_n(q, k, v, attn_mask=mask.cuda(), attn_bias=bias.cuda(), **kw)
+    check_close("O(mask,bias)", out, want, native, dtype)
+    assert out[0, :, 7].abs().max().item() == 0.0
+    # key-padding style mask broadcast over heads and queries, no causal, n = 0
+    pad = torch.ones(B, 1, 1, S, dtype=torch.bool)
+    pad[0, ..., 200:] = False
+    out2 = flash_attention_n(q, k, v, attn_mask=pad.cuda())
+    want2 = orc.slow_attention_n(q.double().cpu(), k.double().cpu(), v.double().cpu(), attn_mask=pad)
+    check_close("O(padding mask)", out2, want2, None, dtype)
+
+
+def test_forward_shared_kv_heads(fasn_lib):
+    """3-D key/value = shared by all heads (flash_attn.py:75-79, intended meaning)."""
+    from flash_attention_softmax_n import flash_attention_n
+    dtype = torch.bfloat16
+    q, k, v, _ = make_qkv(2, 4, 130, 190, 64, dtype, seed=9, heads_kv=1)
+    out = flash_attention_n(q, k[:, 0], v[:, 0], softmax_n_param=1)
+    want = orc.slow_attention_n(q.double().cpu(), k[:, 0].double().cpu(), v[:, 0].double().cpu(), softmax_n_param=1)
+    check_close("O(shared kv)", out, want, None, dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("causal", [False, True])
+def test_forward_dropout_matches_oracle_with_same_mask(fasn_lib, dtype, causal):
+    from flash_attention_softmax_n import flash_attention_n
+    B, H, L, S, D, p = 2, 2, 300, 260, 128, 0.1
+    q, k, v, _ = make_qkv(B, H, L, S, D, dtype, seed=21)
+    seed, offset = 0x5EED, 3
+    out = flash_attention_n(q, k, v, softmax_n_param=0.5, dropout_p=p, is_causal=causal, _philox=(seed, offset))
+    keep = orc.dropout_keep_mask(seed, offset, B, H, L, S, p)
+    want = orc.slow_attention_n(q.double().cpu(), k.double().cpu(), v.double().cpu(), softmax_n_param=0.5,
+                                is_causal=causal, keep_mask=keep, dropout_p=p)
+    check_close("O(dropout)", out, want, None, dtype, rel_scale=1.5)
+    out_b = flash_attention_n(q, k, v, softmax_n_param=0.5, dropout_p=p, is_causal=causal, _philox=(seed, offset + 1))
+    assert not torch.equal(out, out_b)
+
+
+def test_forward_strided_inputs_and_errors(fasn_lib):
+    from flash_attention_softmax_n import flash_attention_n
+    dtype = torch.float16
+    B, H, L, D = 2, 3, 160, 64
+    g = torch.Generator().manual_seed(3)
+    qkv = (torch.randn(B, L, 3, H, D, generator=g) * 0.5).to(dtype).cuda()      # packed (B,L,3,H,D) projection output
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))              # (B,H,L,D) views, row stride 3*H*D
+    out = flash_attention_n(q, k, v, softmax_n_param=1, is_causal=True)
+    want = orc.slow_attention_n(q.double().cpu(), k.double().cpu(), v.double().cpu(), softmax_n_param=1, is_causal=True)
+    check_close("O(strided)", out, want, None, dtype)
+    with pytest.raises(NotImplementedError):
+        flash_attention_n(q.float(), k.float(), v.float())
+    with pytest.raises(NotImplementedError):
+        flash_attention_n(q[..., :32], k[..., :32], v[..., :32])
