@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement for the fused softmax_n attention path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4|c5]
+
+Prints ONE JSON line (rank 0).  A "step" is one pass of the hot path over one batch of synthetic input:
+for the headline workload (BASELINE.json configs[2], "c3": fwd+bwd fp16 B=4 H=32 S=4096 D=128 n=0.5 causal
+dropout 0.1) that is one forward and one backward of `flash_attention_n`, four kernel launches.
+
+  value      whole-job algorithmic TFLOP/s with Q,K,V,dO resident in HBM (CUDA events, max over ranks)
+  e2e        the same metric through the public API with HOST (pinned) buffers: H2D of q,k,v,dO and D2H of
+             o,dq,dk,dv inside the timed region
+  roofline   the dominant kernel (backward main kernel) against the measured bf16 tensor peak
+  cpu_baseline  the oracle port of the reference's slow_attention_n on this box's host cores (bounded sample)
+
+With N > 1 (torchrun), every rank runs the same per-GPU workload on its own resident slab of (batch, head)
+units (weak scaling, no collective on the data path); the time is the max over ranks.
+
+--impl reference times the reference's own CPU implementation of the path (the oracle port: the reference is
+pure Python, there is nothing to compile into oracle/_ref) with all host threads on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "flash-attention-softmax-n_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "attention fwd+bwd TFLOPS/GPU and % tensor-core peak at S=4096 D=128 bf16"
+
+WORKLOADS = {
+    # name: B, H, S, D, dtype, n, causal, dropout, backward
+    "c3": dict(B=4, H=32, S=4096, D=128, dtype="f16", n=0.5, causal=True, dropout=0.1, bwd=True,
+               desc="BASELINE.json configs[2]: fwd+bwd fp16 B=4 H=32 S=4096 D=128 n=0.5 causal dropout=0.1"),
+    "c3bf16": dict(B=4, H=32, S=4096, D=128, dtype="bf16", n=0.5, causal=True, dropout=0.1, bwd=True,
+                   desc="configs[2] in bf16"),
+    "c2": dict(B=8, H=16, S=2048, D=64, dtype="bf16", n=1.0, causal=False, dropout=0.0, bwd=False,
+               desc="BASELINE.json configs[1]: fwd bf16 B=8 H=16 S=2048 D=64 n=1 non-causal"),
+    "c4": dict(B=8, H=40, S=8192, D=128, dtype="bf16", n=1.0, causal=True, dropout=0.0, bwd=False,
+               desc="BASELINE.json configs[3] per-GPU share: fwd bf16 320 (batch,head) units S=8192 D=128 n=1 causal"),
+    "c5": dict(B=1, H=16, S=65536, D=64, dtype="bf16", n=1.0, causal=True, dropout=0.0, bwd=False,
+               desc="BASELINE.json configs[4]: fwd bf16 B=1 H=16 S=65536 D=64 n=1 causal"),
+}
+
+
+def algorithmic_flops(w):
+    """F_fwd = 4 B H Sq Skv D (x 1/2 causal); F_bwd = 2.5 F_fwd."""
+    f = 4.0 * w["B"] * w["H"] * w["S"] * w["S"] * w["D"] * (0.5 if w["causal"] else 1.0)
+    return f, (2.5 * f if w["bwd"] else 0.0)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(burst=float(p["bf16_tflops"]), sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    hbm=float(p["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        self.samples = []
+        if self.proc is None:
+            return
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out = ""
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 9 and f[1].isdigit():
+                self.samples.append(f)
+
+    def summary(self):
+        if not getattr(self, "samples", None):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [int(f[1]) for f in self.samples]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(f[5 + i].lower().startswith("active") for f in self.samples)]
+        pw = [float(f[3]) for f in self.samples if f[3].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": int(self.samples[0][2]), "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of slow_attention_n on the host cores
+# --------------------------------------------------------------------------------------------------------------
+
+def cpu_sample(w, budget_s, threads):
+    """Time fwd(+bwd) of the oracle on single (batch, head) units of the workload, fp32, all host threads.
+    Units are independent, so units/s extrapolates linearly; returns (TFLOP/s, units timed, seconds, description)."""
+    from oracle import attention_oracle as orc
+    torch.set_num_threads(threads)
+    S, D = w["S"], w["D"]
+    rows = S
+    if w["S"] > 8192:                      # c5: the (S x S) score matrix does not fit; time one 4096-row query block
+        rows = 4096
+    g = torch.Generator().manual_seed(1234)
+    q = (torch.randn(1, 1, rows, D, generator=g) * 0.5)
+    k = (torch.randn(1, 1, S, D, generator=g) * 0.5)
+    v = (torch.randn(1, 1, S, D, generator=g) * 0.5)
+    do = torch.randn(1, 1, rows, D, generator=g)
+    keep = None
+    if w["dropout"] > 0:
+        keep = orc.dropout_keep_mask(0x5EED, 0, 1, 1, rows, S, w["dropout"])
+    kw = dict(softmax_n_param=w["n"], is_causal=w["causal"], keep_mask=keep, dropout_p=w["dropout"])
+
+    def one():
+        if w["bwd"]:
+            orc.attention_fwd_bwd(q, k, v, do, dtype=torch.float32, **kw)
+        else:
+            with torch.no_grad():
+                orc.slow_attention_n(q, k, v, **kw)
+
+    one()                                  # warm-up (thread pool, allocator)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        one()
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or n >= 64:
+            break
+    f_fwd, f_bwd = algorithmic_flops(dict(w, B=1, H=1))
+    unit_flops = (f_fwd + f_bwd) * (rows / S if rows != S else 1.0)
+    if rows != S and w["causal"]:          # bottom-right aligned block of `rows` queries sees all S keys minus a triangle
+        unit_flops = 4.0 * D * (rows * S - rows * (rows - 1) / 2.0)
+    tflops = unit_flops * n / el / 1e12
+    desc = (f"{n} x one (batch,head) unit of the workload ({rows} query rows x {S} keys, D={D}, fp32, "
+            f"{'fwd+bwd' if w['bwd'] else 'fwd'}), {el:.1f} s on {threads} threads; units are independent, "
+            f"so whole-workload throughput is the same figure")
+    return tflops, n, el, desc
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = []
+    for _ in range(args.warmup):
+        cpu_sample(w, 0.5, threads)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        tf, n, el, desc = cpu_sample(w, args.cpu_step_seconds, threads)
+        per_step.append((tf, el))
+    wall = time.perf_counter() - t_all
+    tf = sum(t for t, _ in per_step) / len(per_step)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "sample": desc},
+        "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------------
+
+def run_ours(args, w):
+    import torch.distributed as dist
+    from flash_attention_softmax_n import flash_attention_n, _native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the fused kernels have no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    lib = _native.load()
+    dtype = torch.float16 if w["dtype"] == "f16" else torch.bfloat16
+    B, H, S, D = w["B"], w["H"], w["S"], w["D"]
+    units = B * H
+    torch.manual_seed(1234 + rank)
+    # synthetic inputs exactly as the reference's tests draw them: N(0, 0.5^2), dO ~ N(0,1) (tests/common.py:18-20)
+    q = torch.empty(B, H, S, D, device=dev, dtype=dtype).normal_(0, 0.5).requires_grad_(w["bwd"])
+    k = torch.empty(B, H, S, D, device=dev, dtype=dtype).normal_(0, 0.5).requires_grad_(w["bwd"])
+    v = torch.empty(B, H, S, D, device=dev, dtype=dtype).normal_(0, 0.5).requires_grad_(w["bwd"])
+    do = torch.randn(B, H, S, D, device=dev, dtype=dtype)
+    kw = dict(softmax_n_param=w["n"], is_causal=w["causal"], dropout_p=w["dropout"], _bh_offset=rank * units)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if args.flush_l2 else None
+
+    def step(i):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        if w["dropout"] > 0:
+            kw["_philox"] = (0x5EED, i)
+        o = flash_attention_n(q, k, v, **kw)
+        if w["bwd"]:
+            q.grad = k.grad = v.grad = None
+            o.backward(do)
+        return o
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+
+    # ---- timed region: resident inputs -------------------------------------------------------------------
+    lib.fasn_profile(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            step(100 + i)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    fwd_ms, fwd_n, bwd_ms, bwd_n = ctypes.c_double(), ctypes.c_int32(), ctypes.c_double(), ctypes.c_int32()
+    _native.check(lib.fasn_profile_read(ctypes.byref(fwd_ms), ctypes.byref(fwd_n), ctypes.byref(bwd_ms), ctypes.byref(bwd_n)),
+                  "fasn_profile_read")
+    lib.fasn_profile(0)
+    if flush is not None:                   # the flush kernel sits inside the event bracket: measure and subtract it
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+        f1.record()
+        torch.cuda.synchronize()
+        ms -= f0.elapsed_time(f1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = t.item()
+    f_fwd, f_bwd = algorithmic_flops(w)
+    flops_step = f_fwd + f_bwd
+    value = world * flops_step * args.steps / (ms_max * 1e-3) / 1e12
+
+    # ---- end to end: host buffers through the public API ----------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hq, hk, hv, hdo = (torch.empty(B, H, S, D, dtype=dtype).normal_(0, 0.5).pin_memory() for _ in range(4))
+        outs = [torch.empty(B, H, S, D, dtype=dtype).pin_memory() for _ in range(4 if w["bwd"] else 1)]
+
+        def e2e_step(i):
+            dq_, dk_, dv_ = (t_.to(dev, non_blocking=True) for t_ in (hq, hk, hv))
+            if w["bwd"]:
+                dq_.requires_grad_(); dk_.requires_grad_(); dv_.requires_grad_()
+                ddo = hdo.to(dev, non_blocking=True)
+            if w["dropout"] > 0:
+                kw["_philox"] = (0x5EED, 1000 + i)
+            o = flash_attention_n(dq_, dk_, dv_, **kw)
+            outs[0].copy_(o.detach(), non_blocking=True)
+            if w["bwd"]:
+                o.backward(ddo)
+                outs[1].copy_(dq_.grad, non_blocking=True)
+                outs[2].copy_(dk_.grad, non_blocking=True)
+                outs[3].copy_(dv_.grad, non_blocking=True)
+
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        n_e2e = max(3, min(args.steps, 10))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_e2e):
+            e2e_step(i)
+        e1.record()
+        barrier()
+        t2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if distributed:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        nbytes = B * H * S * D * 2
+        e2e = {"value": world * flops_step * n_e2e / (t2.item() * 1e-3) / 1e12, "unit": "TFLOP/s",
+               "h2d_bytes_per_step": nbytes * (4 if w["bwd"] else 3), "d2h_bytes_per_step": nbytes * len(outs),
+               "ms_per_step": t2.item() / n_e2e, "steps": n_e2e}
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------------------
+    peaks = measured_peaks()
+    if w["bwd"] and bwd_n.value > 0:
+        k_ms, k_flops, k_name = bwd_ms.value / bwd_n.value, f_bwd, "fasn_bwd_kernel (backward main)"
+    else:
+        k_ms, k_flops, k_name = fwd_ms.value / max(fwd_n.value, 1), f_fwd, "fasn_fwd_kernel"
+    achieved = k_flops / (k_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["sustained"], "traffic": None, "kernel": k_name, "kernel_ms": k_ms,
+                "peak_kind": "sustained bf16 dense, " + peaks["source"], "frac_of_burst_peak": achieved / peaks["burst"],
+                "fwd_kernel_ms": fwd_ms.value / max(fwd_n.value, 1),
+                "fwd_kernel_tflops": f_fwd / (fwd_ms.value / max(fwd_n.value, 1) * 1e-3) / 1e12 if fwd_n.value else None}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            tf, n, el, desc = cpu_sample(w, args.cpu_seconds, os.cpu_count() or 1)
+            cpu = {"value": tf, "unit": "TFLOP/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": desc}
+        line = {
+            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": w["dtype"], "data": "synthetic",
+            "config": {"workload": w["desc"], "per_gpu_units": units, "parallelism": f"batch x head sharded over {world} GPU(s), no data-path collective",
+                       "l2": "flush between steps (256 MiB write)" if args.flush_l2 else
+                             f"working set {(8 if w['bwd'] else 4) * B * H * S * D * 2 / 2**20:.0f} MiB per step > 126 MB L2, no flush"},
+            "per_gpu_tflops": value / world, "frac_of_peak": value / world / peaks["sustained"],
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks.summary(),
+            "gpu_launches": world * args.steps * ((1 + 3) if w["bwd"] else 1),
+        }
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--flush-l2", action="store_true", help="write 256 MiB between steps (default for small workloads)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget inside the default run")
+    ap.add_argument("--cpu-step-seconds", type=float, default=6.0, help="--impl reference: CPU seconds per step")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.workload == "c2":
+        args.flush_l2 = True               # 134 MB working set ~ L2 size
+    if args.impl == "reference":
+        args.cpu_step_seconds = min(args.cpu_step_seconds, 150.0 / max(args.steps, 1))   # whole run within a few minutes
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/fasn.h"
 #include "fasn_common.cuh"
@@ -66,6 +67,24 @@ int make_map(CUtensorMap* m, const void* ptr, long long sb, long long sh, long l
   return 0;
 }
 
+// Launches (and cuTensorMapEncodeTiled, a driver call) need the context of the device that owns the tensors to be
+// current on the calling thread.  Callers such as PyTorch's autograd worker threads may not have bound one yet
+// (allocations served from a cache never touch the runtime), so bind it here and restore the previous device.
+struct DeviceGuard {
+  int prev = -1, dev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(const void* device_ptr) {
+    cudaPointerAttributes at{};
+    err = cudaPointerGetAttributes(&at, device_ptr);
+    if (err != cudaSuccess) return;
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) { err = cudaErrorInvalidDevicePointer; return; }
+    dev = at.device;
+    if ((err = cudaGetDevice(&prev)) != cudaSuccess) return;
+    err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+
 int check_common(const FasnParams* p) {
   if (p == nullptr) return fail(FASN_EINVAL, "params is null");
   if (p->struct_size != sizeof(FasnParams)) return fail(FASN_EINVAL, "struct_size %u != sizeof(FasnParams) %zu", p->struct_size, sizeof(FasnParams));
@@ -80,6 +99,35 @@ int check_common(const FasnParams* p) {
   if (p->lse == nullptr) return fail(FASN_EINVAL, "lse is null");
   return 0;
 }
+
+// Optional per-kernel timing (fasn_profile): CUDA event pairs recorded around the two tensor-core kernels on the
+// caller's stream, read back (and cleared) by fasn_profile_read after the caller has synchronised.
+struct EventPair { cudaEvent_t a, b; };
+struct Profile {
+  std::mutex mu;
+  bool enabled = false;
+  std::vector<EventPair> fwd, bwd;
+};
+Profile g_prof;
+
+struct ScopedEvents {
+  std::vector<EventPair>* sink = nullptr;
+  EventPair ev{};
+  cudaStream_t st;
+  ScopedEvents(std::vector<EventPair>& v, cudaStream_t s) : st(s) {
+    std::lock_guard<std::mutex> l(g_prof.mu);
+    if (!g_prof.enabled) return;
+    if (cudaEventCreate(&ev.a) != cudaSuccess || cudaEventCreate(&ev.b) != cudaSuccess) return;
+    sink = &v;
+    cudaEventRecord(ev.a, st);
+  }
+  ~ScopedEvents() {
+    if (!sink) return;
+    cudaEventRecord(ev.b, st);
+    std::lock_guard<std::mutex> l(g_prof.mu);
+    sink->push_back(ev);
+  }
+};
 
 fasn::AuxView aux_view(const FasnAux& a) { return fasn::AuxView{a.ptr, a.stride_b, a.stride_h, a.stride_q}; }
 fasn::TensorView tensor_view(const FasnTensor& t) { return fasn::TensorView{t.ptr, t.stride_b, t.stride_h, t.stride_s}; }
@@ -105,6 +153,9 @@ const char* fasn_last_error(void) { return g_last_error.c_str(); }
 
 int fasn_fwd(const FasnParams* p) {
   if (int rc = check_common(p)) return rc;
+  if (p->q.ptr == nullptr) return fail(FASN_EINVAL, "q: null pointer");
+  DeviceGuard guard(p->q.ptr);
+  if (guard.err != cudaSuccess) return fail_cuda(guard.err, "q is not a device pointer / cannot bind its device");
   const bool bf16 = p->dtype == FASN_BF16;
   const int B = p->batch, H = p->heads, Hkv = p->heads_kv, L = p->seqlen_q, S = p->seqlen_kv, D = p->head_dim;
   CUtensorMap tq, tk, tv, to;
@@ -125,7 +176,11 @@ int fasn_fwd(const FasnParams* p) {
   a.inv_keep = 1.0f / (1.0f - p->dropout_p);
   a.key = philox_key(p->philox_seed, p->philox_offset);
   a.bh_offset = (uint32_t)p->bh_offset;
-  cudaError_t e = fasn::launch_fwd(D, bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tk, tv, to, a, (cudaStream_t)p->stream);
+  cudaError_t e;
+  {
+    ScopedEvents prof(g_prof.fwd, (cudaStream_t)p->stream);
+    e = fasn::launch_fwd(D, bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tk, tv, to, a, (cudaStream_t)p->stream);
+  }
   if (e != cudaSuccess) return fail_cuda(e, "fasn_fwd launch");
   return 0;
 }
@@ -141,7 +196,9 @@ int fasn_bwd_workspace(const FasnParams* p, uint64_t* delta_bytes, uint64_t* dq_
 int fasn_bwd(const FasnParams* p) {
   if (int rc = check_common(p)) return rc;
   if (p->delta == nullptr || p->dq_accum == nullptr) return fail(FASN_EINVAL, "delta / dq_accum workspace is null");
-  if (p->dq.ptr == nullptr) return fail(FASN_EINVAL, "dq is null");
+  if (p->dq.ptr == nullptr || p->q.ptr == nullptr) return fail(FASN_EINVAL, "q / dq is null");
+  DeviceGuard guard(p->q.ptr);
+  if (guard.err != cudaSuccess) return fail_cuda(guard.err, "q is not a device pointer / cannot bind its device");
   const bool bf16 = p->dtype == FASN_BF16;
   const int B = p->batch, H = p->heads, Hkv = p->heads_kv, L = p->seqlen_q, S = p->seqlen_kv, D = p->head_dim;
   CUtensorMap tq, tk, tv, tdo, tdk, tdv;
@@ -170,10 +227,41 @@ int fasn_bwd(const FasnParams* p) {
   cudaStream_t st = (cudaStream_t)p->stream;
   cudaError_t e = fasn::launch_bwd_prep(D, bf16, tensor_view(p->o), tensor_view(p->dout), a, st);
   if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd prep launch");
-  e = fasn::launch_bwd(D, bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tk, tv, tdo, tdk, tdv, a, tensor_view(p->dk), tensor_view(p->dv), st);
+  {
+    ScopedEvents prof(g_prof.bwd, st);
+    e = fasn::launch_bwd(D, bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tk, tv, tdo, tdk, tdv, a, tensor_view(p->dk), tensor_view(p->dv), st);
+  }
   if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd main launch");
   e = fasn::launch_bwd_finish(D, bf16, tensor_view(p->dq), a, st);
   if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd finish launch");
+  return 0;
+}
+
+int fasn_profile(int enable) {
+  std::lock_guard<std::mutex> l(g_prof.mu);
+  g_prof.enabled = enable != 0;
+  return 0;
+}
+
+int fasn_profile_read(double* fwd_ms, int32_t* fwd_launches, double* bwd_ms, int32_t* bwd_launches) {
+  if (!fwd_ms || !fwd_launches || !bwd_ms || !bwd_launches) return fail(FASN_EINVAL, "null argument");
+  std::lock_guard<std::mutex> l(g_prof.mu);
+  auto drain = [](std::vector<EventPair>& v, double* ms, int32_t* n) -> cudaError_t {
+    *ms = 0.0; *n = 0;
+    cudaError_t err = cudaSuccess;
+    for (auto& e : v) {
+      float t = 0.f;
+      cudaError_t r = cudaEventElapsedTime(&t, e.a, e.b);
+      if (r == cudaSuccess) { *ms += t; *n += 1; } else err = r;
+      cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    v.clear();
+    return err;
+  };
+  cudaError_t e1 = drain(g_prof.fwd, fwd_ms, fwd_launches);
+  cudaError_t e2 = drain(g_prof.bwd, bwd_ms, bwd_launches);
+  if (e1 != cudaSuccess) return fail_cuda(e1, "fasn_profile_read (forward events; synchronise the stream first)");
+  if (e2 != cudaSuccess) return fail_cuda(e2, "fasn_profile_read (backward events; synchronise the stream first)");
   return 0;
 }
 
@@ -191,6 +279,8 @@ int fasn_probe(int mode, uint32_t dtype, const void* x, const void* y, float* c,
   if (mode < 0 || mode > 3 || x == nullptr || y == nullptr || c == nullptr) return fail(FASN_EINVAL, "bad argument");
   if (dtype != FASN_FP16 && dtype != FASN_BF16) return fail(FASN_EUNSUPPORTED, "dtype");
   const bool bf16 = dtype == FASN_BF16;
+  DeviceGuard guard(x);
+  if (guard.err != cudaSuccess) return fail_cuda(guard.err, "x is not a device pointer / cannot bind its device");
   CUtensorMap tx, ty;
   if (int rc = make_map(&tx, x, 0, 0, 128, 1, 1, 128, 128, bf16, "x")) return rc;
   if (int rc = make_map(&ty, y, 0, 0, 128, 1, 1, 128, 128, bf16, "y")) return rc;

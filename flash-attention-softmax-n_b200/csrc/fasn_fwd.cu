@@ -109,7 +109,7 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 8) {
-    setmaxnreg_dec<64>();
+    setmaxnreg_dec<48>();   // 256 x 224 + 128 x 48 = 63488 <= 384 x 168 registers granted at launch
     if (warp == 8) {
       // ------------------------------------------------------------------ TMA producer
       if (lane == 0) {

@@ -89,12 +89,16 @@ FASN_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Wait until the phase with the given parity has completed.  A watchdog turns a protocol bug into a
-// trap (launch failure) instead of a hung GPU: 2^26 polls of a HW-sleeping try_wait is >> any legal wait.
+// trap (launch failure) instead of a hung GPU: every legal wait in these kernels is bounded by a few tile
+// times (microseconds), 2^22 polls of a HW-suspending try_wait is seconds.
+#ifndef FASN_WATCHDOG_POLLS
+#define FASN_WATCHDOG_POLLS (1u << 22)
+#endif
 FASN_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifndef FASN_NO_WATCHDOG
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) { __trap(); }
+    if (++spins > FASN_WATCHDOG_POLLS) { __trap(); }
   }
 #else
   while (!mbar_try_wait(bar, parity)) {}

@@ -106,6 +106,13 @@ int fasn_bwd(const FasnParams* p);
 /* Bytes the caller must provide for FasnParams.delta and FasnParams.dq_accum. */
 int fasn_bwd_workspace(const FasnParams* p, uint64_t* delta_bytes, uint64_t* dq_accum_bytes);
 
+/* Kernel timing for roofline reports: while enabled, fasn_fwd and fasn_bwd bracket their tensor-core kernel
+ * (the forward kernel / the main backward kernel) with CUDA events on the caller's stream.
+ * fasn_profile_read returns the summed durations (ms) and launch counts since the last read and clears them;
+ * the caller must have synchronised the stream(s) first. */
+int fasn_profile(int enable);
+int fasn_profile_read(double* fwd_ms, int32_t* fwd_launches, double* bwd_ms, int32_t* bwd_launches);
+
 /* Test hook: write the dropout keep mask the kernels use, as (B,H,L,S) uint8 (1 = keep), to `out`. */
 int fasn_dropout_mask(uint8_t* out, int32_t batch, int32_t heads, int32_t seqlen_q, int32_t seqlen_kv,
                       float dropout_p, uint64_t philox_seed, uint64_t philox_offset, int64_t bh_offset,
