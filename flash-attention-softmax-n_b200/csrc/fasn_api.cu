@@ -85,6 +85,21 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
 };
 
+// (D, Sqp, B*H, 1) fp32 accumulator, box = 32 x 128 x 1 x 1 (128-byte rows), 128-byte swizzle: target of the TMA reduce-add
+int make_accum_map(CUtensorMap* m, float* ptr, long long BH, int Sqp, int D) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return fail(FASN_EDRIVER, "cuTensorMapEncodeTiled is not available from this driver");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(FASN_EUNSUPPORTED, "dq_accum: pointer is not 16-byte aligned");
+  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)Sqp, (cuuint64_t)BH, 1};
+  cuuint64_t strides[3] = {(cuuint64_t)D * 4, (cuuint64_t)Sqp * D * 4, (cuuint64_t)BH * Sqp * D * 4};
+  cuuint32_t box[4] = {32, 128, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FASN_EDRIVER, "dq_accum: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
 int check_common(const FasnParams* p) {
   if (p == nullptr) return fail(FASN_EINVAL, "params is null");
   if (p->struct_size != sizeof(FasnParams)) return fail(FASN_EINVAL, "struct_size %u != sizeof(FasnParams) %zu", p->struct_size, sizeof(FasnParams));
@@ -209,11 +224,14 @@ int fasn_bwd(const FasnParams* p) {
   if (int rc = make_map(&tdk, p->dk.ptr, p->dk.stride_b, p->dk.stride_h, p->dk.stride_s, B, H, S, D, bf16, "dk")) return rc;
   if (int rc = make_map(&tdv, p->dv.ptr, p->dv.stride_b, p->dv.stride_h, p->dv.stride_s, B, H, S, D, bf16, "dv")) return rc;
   if (p->o.ptr == nullptr) return fail(FASN_EINVAL, "o is null");
+  CUtensorMap tdq;
+  if (int rc = make_accum_map(&tdq, p->dq_accum, (long long)B * H, (L + 127) / 128 * 128, D)) return rc;
   fasn::BwdArgs a{};
   a.B = B; a.H = H; a.Hkv = Hkv; a.Sq = L; a.Skv = S;
   a.causal_off = S - L;
-  a.scale = p->scale;
+  a.scale = p->scale / (1.0f - p->dropout_p);
   a.scale_log2 = p->scale * fasn::kLog2e;
+  a.keep_prob = 1.0f - p->dropout_p;
   a.lse = p->lse;
   a.delta = p->delta;
   a.dq_accum = p->dq_accum;
@@ -229,7 +247,7 @@ int fasn_bwd(const FasnParams* p) {
   if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd prep launch");
   {
     ScopedEvents prof(g_prof.bwd, st);
-    e = fasn::launch_bwd(D, bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tk, tv, tdo, tdk, tdv, a, tensor_view(p->dk), tensor_view(p->dv), st);
+    e = fasn::launch_bwd(D, bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tk, tv, tdo, tdk, tdv, tdq, a, tensor_view(p->dk), tensor_view(p->dv), st);
   }
   if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd main launch");
   e = fasn::launch_bwd_finish(D, bf16, tensor_view(p->dq), a, st);

@@ -13,14 +13,14 @@
 //                                 S^T columns: [0,32) and [64,96)), B = dO_i MN-major        -> TMEM [256,256+D)
 //   dK  += dS^T Q_i               SS-MMA, A = dS^T in smem (K-major),    B = Q_i MN-major   -> TMEM [256+D,256+2D)
 //   dQ_i = dS K                   SS-MMA, A = the same smem tile read MN-major, B = K MN-major -> TMEM [128,128+D)
-//                                 (aliases dP^T), then reduced into the fp32 dq_accum with red.global.add.v4.f32
+//                                 (aliases dP^T), then added into the fp32 dq_accum by TMA reduce-add (cp.reduce.async.bulk.tensor)
 //
 // The only difference from softmax_0 attention is that P is recomputed from LSE_n = ln(n + sum exp s) (SURVEY.md
 // section 9): the Jacobian keeps the softmax form dS = P o (dP - delta) with delta_i = sum_d O_id dO_id.
 //
 //   warps 0-7   compute: warp w owns TMEM lanes 32(w%4).. (kv rows) and q-columns 64(w/4)..64(w/4)+63
-//   warps 8-11  dQ reducers: TMEM -> registers -> red.global.add
-//   warp 12     TMA producer (K,V once; Q_i + LSE2 and dO_i + delta through 2-deep rings)
+//   warps 8-11  dQ reducers: TMEM -> registers -> fp32 staging in smem -> TMA reduce-add
+//   warp 12     TMA producer (K,V once; Q_i + LSE2 + delta through a 2-deep ring, dO_i single-buffered)
 //   warp 13     MMA issuer (one thread)        warp 14  TMEM allocator        warp 15  idle
 #include "fasn_common.cuh"
 #include "fasn_ptx.cuh"
@@ -37,9 +37,20 @@ template <int D> struct BwdCfg {
   static constexpr int BLK_BYTES = 128 * 128;
   static constexpr int DS_BYTES = 2 * BLK_BYTES;                  // dS^T: [2 q-blocks][128 kv rows][128 B]
   static constexpr int NUM_BARS = 20;
-  // K, V, Q ring (2), dO ring (2), dS^T, LSE2 ring + delta ring (2 x 2 x 512 B), barriers, tmem slot
-  static constexpr int SMEM_BYTES = 6 * TILE_BYTES + DS_BYTES + 4 * 512 + NUM_BARS * 8 + 16;
+  static constexpr int DQ_STAGE_BYTES = 128 * 32 * 4;             // dQ staging chunk: 128 rows x 32 fp32 columns
+  // K, V, Q ring (2), dO (1), dS^T, dQ staging (2 chunks), LSE2 ring + delta ring (2 x 2 x 512 B), barriers, tmem slot
+  static constexpr int SMEM_BYTES = 5 * TILE_BYTES + DS_BYTES + 2 * DQ_STAGE_BYTES + 4 * 512 + NUM_BARS * 8 + 16;
 };
+
+// TMA reduce-add shared -> global (fp32 tile added into the tensor at L2), bulk async-group completion
+FASN_DEVICE void tma_reduce_add_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+template <int N> FASN_DEVICE void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
 
 // cp.async.bulk 1-D global -> shared with mbarrier completion
 FASN_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -52,7 +63,8 @@ template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                const __grid_constant__ CUtensorMap tm_dk, const __grid_constant__ CUtensorMap tm_dv, const BwdArgs a,
+                const __grid_constant__ CUtensorMap tm_dk, const __grid_constant__ CUtensorMap tm_dv,
+                const __grid_constant__ CUtensorMap tm_dq, const BwdArgs a,
                 const TensorView dk_view, const TensorView dv_view) {
   using Cfg = BwdCfg<D>;
   constexpr int DB = Cfg::DB, TILE_BYTES = Cfg::TILE_BYTES, BLK_BYTES = Cfg::BLK_BYTES;
@@ -94,16 +106,17 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* sK = smem;
   uint8_t* sV = sK + TILE_BYTES;
   uint8_t* sQ = sV + TILE_BYTES;              // [2]
-  uint8_t* sDO = sQ + 2 * TILE_BYTES;         // [2]
-  uint8_t* sDS = sDO + 2 * TILE_BYTES;
-  float* sLse = reinterpret_cast<float*>(sDS + Cfg::DS_BYTES);   // [2][128]
+  uint8_t* sDO = sQ + 2 * TILE_BYTES;         // [1]
+  uint8_t* sDS = sDO + TILE_BYTES;
+  uint8_t* sDQ = sDS + Cfg::DS_BYTES;         // [2] fp32 staging chunks for the TMA reduce-add of dQ
+  float* sLse = reinterpret_cast<float*>(sDQ + 2 * Cfg::DQ_STAGE_BYTES);   // [2][128]
   float* sDelta = sLse + 256;                                    // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
   uint64_t* kv_full = bars + 0;
   uint64_t* q_full = bars + 1;     // [2]
   uint64_t* q_empty = bars + 3;    // [2]
-  uint64_t* do_full = bars + 5;    // [2]
-  uint64_t* do_empty = bars + 7;   // [2]
+  uint64_t* do_full = bars + 5;
+  uint64_t* do_empty = bars + 7;
   uint64_t* s_full = bars + 9;
   uint64_t* dp_full = bars + 10;
   uint64_t* p_full = bars + 11;    // 256 arrivals
@@ -116,11 +129,12 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   if (warp == 12 && lane == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
-    tma_prefetch_desc(&tm_dk); tma_prefetch_desc(&tm_dv);
+    tma_prefetch_desc(&tm_dk); tma_prefetch_desc(&tm_dv); tma_prefetch_desc(&tm_dq);
   }
   if (warp == 13 && lane == 0) {
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&do_full[i], 1); mbar_init(&do_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    mbar_init(do_full, 1); mbar_init(do_empty, 1);
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(ds_empty, 1);
     mbar_init(dq_full, 1); mbar_init(dq_empty, 128); mbar_init(dkv_full, 1);
     fence_mbar_init();
@@ -148,15 +162,15 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t ph = (it >> 1) & 1;
         const int qi0 = (i_start + it) * 128;
         mbar_wait(&q_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&q_full[s], TILE_BYTES + 512);
+        mbar_arrive_expect_tx(&q_full[s], TILE_BYTES + 1024);
 #pragma unroll
         for (int db = 0; db < DB; ++db) tma_load_4d(sQ + s * TILE_BYTES + db * BLK_BYTES, &tm_q, &q_full[s], db * 64, qi0, h, b);
         bulk_load_1d(sLse + s * 128, lse2 + (long long)bh * a.Sqp + qi0, 512, &q_full[s]);
-        mbar_wait(&do_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&do_full[s], TILE_BYTES + 512);
+        bulk_load_1d(sDelta + s * 128, a.delta + (long long)bh * a.Sqp + qi0, 512, &q_full[s]);
+        mbar_wait(do_empty, (it & 1) ^ 1);     // single dO buffer: free once dV of the previous tile has completed
+        mbar_arrive_expect_tx(do_full, TILE_BYTES);
 #pragma unroll
-        for (int db = 0; db < DB; ++db) tma_load_4d(sDO + s * TILE_BYTES + db * BLK_BYTES, &tm_do, &do_full[s], db * 64, qi0, h, b);
-        bulk_load_1d(sDelta + s * 128, a.delta + (long long)bh * a.Sqp + qi0, 512, &do_full[s]);
+        for (int db = 0; db < DB; ++db) tma_load_4d(sDO + db * BLK_BYTES, &tm_do, do_full, db * 64, qi0, h, b);
       }
     } else if (warp == 13 && lane == 0) {
       // ---------------------------------------------------------------- MMA issuer
@@ -177,7 +191,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_after();
       issue_kmajor(TM_S, sK_u, sQ_u);
       tc_commit(s_full);
-      mbar_wait(&do_full[0], 0);
+      mbar_wait(do_full, 0);
       tc_fence_after();
       issue_kmajor(TM_DP, sV_u, sDO_u);
       tc_commit(dp_full);
@@ -192,7 +206,8 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb)
           umma_ts(tmem_base + TM_DV, tmem_base + TM_S + (kb >> 2) * 64 + (kb & 3) * 8,
-                  umma_smem_desc(sDO_u + s * TILE_BYTES + kb * 2048, BLK_BYTES, 1024), idesc_dv, (it > 0 || kb > 0) ? 1u : 0u);
+                  umma_smem_desc(sDO_u + kb * 2048, BLK_BYTES, 1024), idesc_dv, (it > 0 || kb > 0) ? 1u : 0u);
+        tc_commit(do_empty);         // dO_i is dead once dP^T_i (issued earlier) and dV_i have completed
         // S^T of the next Q tile (overwrites P^T: ordered behind the dV MMAs on the tensor pipe)
         if (more) {
           mbar_wait(&q_full[s1], ph1);
@@ -209,8 +224,8 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           umma_ss(tmem_base + TM_DK, umma_smem_desc(sDS_u + off, 16, 1024),
                   umma_smem_desc(sQ_u + s * TILE_BYTES + kb * 2048, BLK_BYTES, 1024), idesc_dk, (it > 0 || kb > 0) ? 1u : 0u);
         }
-        tc_commit(&q_empty[s]);      // Q_i, LSE2_i, dO_i and delta_i stay valid until the compute warps are done with
-        tc_commit(&do_empty[s]);     // tile i (ds_full above) and the MMAs that read them have completed
+        tc_commit(&q_empty[s]);      // Q_i, LSE2_i and delta_i stay valid until the compute warps are done with tile i
+                                     // (ds_full above) and the MMAs that read Q_i have completed
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb)
           umma_ss(tmem_base + TM_DQ, umma_smem_desc(sDS_u + kb * 2048, BLK_BYTES, 1024), umma_smem_desc(sK_u + kb * 2048, BLK_BYTES, 1024),
@@ -219,10 +234,10 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_commit(ds_empty);
         // dP^T of the next tile reuses the dQ columns: wait until the reducers have drained dQ_i
         if (more) {
-          mbar_wait(&do_full[s1], ph1);
+          mbar_wait(do_full, (it + 1) & 1);
           mbar_wait(dq_empty, it & 1);
           tc_fence_after();
-          issue_kmajor(TM_DP, sV_u, sDO_u + s1 * TILE_BYTES);
+          issue_kmajor(TM_DP, sV_u, sDO_u);
           tc_commit(dp_full);
         }
       }
@@ -230,28 +245,37 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ dQ reducers
+    // TMEM -> registers -> swizzled fp32 staging chunk in smem -> TMA reduce-add into dq_accum (the L2 does the adds
+    // a full 128-byte line at a time; per-thread red.global instructions are an order of magnitude slower here).
     setmaxnreg_dec<104>();
     const int r = (warp & 3) * 32 + lane;                 // query row inside the tile
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    constexpr int NCH = D / 32;                           // 32-column chunks per dQ tile
     for (int it = 0; it < n_iter; ++it) {
-      const int qrow = (i_start + it) * 128 + r;
-      float* dst = a.dq_accum + ((long long)bh * a.Sqp + qrow) * D;
+      const int qi0 = (i_start + it) * 128;
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
 #pragma unroll
-      for (int hb = 0; hb < D / 64; ++hb) {
-        uint32_t v[64];
-        tmem_ld_x32(tmem_base + lane_off + TM_DQ + hb * 64, v);
-        tmem_ld_x32(tmem_base + lane_off + TM_DQ + hb * 64 + 32, v + 32);
+      for (int ch = 0; ch < NCH; ++ch) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + lane_off + TM_DQ + ch * 32, v);
         tmem_wait_ld();
-        if (hb == D / 64 - 1) { tc_fence_before(); mbar_arrive(dq_empty); }
-        if (qrow < a.Sq) {
+        if (ch == NCH - 1) { tc_fence_before(); mbar_arrive(dq_empty); }    // dQ columns may be overwritten by dP^T now
+        uint8_t* stage = sDQ + (ch & 1) * Cfg::DQ_STAGE_BYTES;
+        if (threadIdx.x == 256) tma_store_wait_read<1>();                   // the reduce issued two chunks ago has read this buffer
+        named_bar_sync(2, 128);
 #pragma unroll
-          for (int i = 0; i < 64; i += 4)
-            red_add_v4(dst + hb * 64 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(stage + r * 128 + ((g ^ (r & 7)) << 4)) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (threadIdx.x == 256) {
+          tma_reduce_add_4d(&tm_dq, stage, ch * 32, qi0, bh, 0);
+          tma_store_commit();
         }
       }
     }
+    if (threadIdx.x == 256) tma_store_wait_all();
   } else {
     // -------------------------------------------------------------------- compute warps
     setmaxnreg_inc<176>();
@@ -260,7 +284,6 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int r = quarter * 32 + lane;                     // kv row inside the tile
     const int kv_row = k0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t lane_bit = 1u << lane;
     const bool kv_valid = kv_row < a.Skv;
     const bool has_aux = (a.mask.ptr != nullptr) || (a.bias.ptr != nullptr);
     const int kv_c = min(kv_row, a.Skv - 1);
@@ -269,19 +292,24 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t bh_global = a.bh_offset + bh;
     const uint32_t kvw = (uint32_t)(kv_row >> 5);          // identical for the 32 lanes of this warp
 
+    const bool kv_tail = (k0 + 128 > a.Skv);               // this K/V tile has rows beyond Skv
+    const float2 c2 = make_float2(a.scale_log2, a.scale_log2);
+
     for (int it = 0; it < n_iter; ++it) {
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       const int qi0 = (i_start + it) * 128;
       const int qc0 = qi0 + half * 64;                     // first query column of this thread
-      uint32_t kw0 = 0xFFFFFFFFu, kw1 = 0xFFFFFFFFu;
+      // keep0 / keep1: bit c = keep decision for (query qc0 + c [+32], this thread's kv row)
+      uint32_t keep0 = 0xFFFFFFFFu, keep1 = 0xFFFFFFFFu;
       if constexpr (DROPOUT) {
-        // lane L generates the keep words of query rows qc0+L and qc0+32+L (all 32 kv rows of this warp)
-        kw0 = dropout_keep_word(a.key, bh_global, (uint32_t)(qc0 + lane), kvw, a.drop_thr);
-        kw1 = dropout_keep_word(a.key, bh_global, (uint32_t)(qc0 + 32 + lane), kvw, a.drop_thr);
+        // lane L generates the 32-key keep words of query rows qc0+L and qc0+32+L; a 32x32 bit transpose across the
+        // warp then hands every lane (= kv row) its own bit of all 64 query columns
+        keep0 = warp_transpose_bits(dropout_keep_word(a.key, bh_global, (uint32_t)(qc0 + lane), kvw, a.drop_thr), lane);
+        keep1 = warp_transpose_bits(dropout_keep_word(a.key, bh_global, (uint32_t)(qc0 + 32 + lane), kvw, a.drop_thr), lane);
       }
-      // ---- P^T
-      mbar_wait(&q_full[s], ph);          // LSE2 of this tile has landed (same barrier as Q_i)
+      // ---- P^T = 2^(S^T c - LSE2)
+      mbar_wait(&q_full[s], ph);          // LSE2 and delta of this tile have landed (same barrier as Q_i)
       mbar_wait(s_full, it & 1);
       tc_fence_after();
       float p[64];
@@ -292,35 +320,41 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_wait_ld();
       }
       const float* lse_s = sLse + s * 128 + half * 64;
-      const bool diag = CAUSAL && (qi0 + a.causal_off < k0 + 127);     // some (q, kv) of this tile pair is above the diagonal
+      if (has_aux) {
+        // generic path: bias added / mask applied in the log2 domain before the exponent
 #pragma unroll
-      for (int c = 0; c < 64; c += 4) {
-        const float4 l4 = *reinterpret_cast<const float4*>(lse_s + c);
-        const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float x = p[c + u] * a.scale_log2;
-          if (has_aux) {
-            const long long q_c = min(qc0 + c + u, a.Sq - 1);
-            if (bbase) x = fmaf(cvt16_to_f32<BF16>(bbase[q_c * a.bias.sq]), kLog2e, x);
-            if (mbase && mbase[q_c * a.mask.sq] == 0) x = -INFINITY;
-          }
-          float e = ex2(x - lv[u]);
-          bool ok = kv_valid;
-          if (diag) ok = ok && (kv_row <= qc0 + c + u + a.causal_off);
-          p[c + u] = ok ? e : 0.f;
+        for (int c = 0; c < 64; ++c) {
+          float x = p[c] * a.scale_log2;
+          const long long q_c = min(qc0 + c, a.Sq - 1);
+          if (bbase) x = fmaf(cvt16_to_f32<BF16>(bbase[q_c * a.bias.sq]), kLog2e, x);
+          if (mbase && mbase[q_c * a.mask.sq] == 0) x = -INFINITY;
+          p[c] = ex2(x - lse_s[c]);
         }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(lse_s + c);
+          const float2 a01 = __ffma2_rn(make_float2(p[c], p[c + 1]), c2, make_float2(-l4.x, -l4.y));
+          const float2 a23 = __ffma2_rn(make_float2(p[c + 2], p[c + 3]), c2, make_float2(-l4.z, -l4.w));
+          p[c] = ex2(a01.x); p[c + 1] = ex2(a01.y); p[c + 2] = ex2(a23.x); p[c + 3] = ex2(a23.y);
+        }
+      }
+      const bool diag = CAUSAL && (qi0 + a.causal_off < k0 + 127);     // some (q, kv) of this tile pair lies above the diagonal
+      if (diag || kv_tail) {
+        // column c is visible to this kv row iff kv_row <= q + off  <=>  c >= kv_row - off - qc0
+        const int first_c = (diag ? max(kv_row - a.causal_off - qc0, 0) : 0) + (kv_valid ? 0 : 64);
+#pragma unroll
+        for (int c = 0; c < 64; ++c) p[c] = (c >= first_c) ? p[c] : 0.f;
       }
       {
         uint32_t pk[32];
 #pragma unroll
         for (int c = 0; c < 64; c += 2) {
           float x0 = p[c], x1 = p[c + 1];
-          if constexpr (DROPOUT) {
-            const uint32_t w0 = __shfl_sync(0xffffffffu, (c < 32) ? kw0 : kw1, c & 31);
-            const uint32_t w1 = __shfl_sync(0xffffffffu, (c < 32) ? kw0 : kw1, (c + 1) & 31);
-            x0 = (w0 & lane_bit) ? x0 * a.inv_keep : 0.f;
-            x1 = (w1 & lane_bit) ? x1 * a.inv_keep : 0.f;
+          if constexpr (DROPOUT) {      // the 1/(1-p) factor of the kept entries is applied to dV in the epilogue
+            const uint32_t w = (c < 32) ? keep0 : keep1;
+            x0 = (w & (1u << (c & 31))) ? x0 : 0.f;
+            x1 = (w & (1u << ((c + 1) & 31))) ? x1 : 0.f;
           }
           pk[c >> 1] = pack2<BF16>(x0, x1);
         }
@@ -329,8 +363,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(p_full);
-      // ---- dS^T
-      mbar_wait(&do_full[s], ph);         // delta of this tile has landed (same barrier as dO_i)
+      // ---- dS'^T = P^T o (Z dP^T - (1-p) delta)      (dS = dS' / (1-p); the factor is folded into the dK / dQ scales)
       mbar_wait(dp_full, it & 1);
       tc_fence_after();
       mbar_wait(ds_empty, (it & 1) ^ 1);  // MMAs of the previous iteration no longer read the dS^T tile
@@ -344,19 +377,20 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
           const float4 d4 = *reinterpret_cast<const float4*>(del_s + g * 32 + c);
-          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-          float ds[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float dp = __uint_as_float(dpr[c + u]);
-            if constexpr (DROPOUT) {
-              const uint32_t w = __shfl_sync(0xffffffffu, (g == 0) ? kw0 : kw1, c + u);
-              dp = (w & lane_bit) ? dp * a.inv_keep : 0.f;
-            }
-            ds[u] = p[g * 32 + c + u] * (dp - dv[u]);
+          float dp0 = __uint_as_float(dpr[c]), dp1 = __uint_as_float(dpr[c + 1]), dp2 = __uint_as_float(dpr[c + 2]), dp3 = __uint_as_float(dpr[c + 3]);
+          if constexpr (DROPOUT) {
+            const uint32_t w = (g == 0) ? keep0 : keep1;
+            dp0 = (w & (1u << (c + 0))) ? dp0 : 0.f;
+            dp1 = (w & (1u << (c + 1))) ? dp1 : 0.f;
+            dp2 = (w & (1u << (c + 2))) ? dp2 : 0.f;
+            dp3 = (w & (1u << (c + 3))) ? dp3 : 0.f;
           }
-          out[(c >> 1)] = pack2<BF16>(ds[0], ds[1]);
-          out[(c >> 1) + 1] = pack2<BF16>(ds[2], ds[3]);
+          const float2 e01 = __fadd2_rn(make_float2(dp0, dp1), make_float2(-d4.x, -d4.y));
+          const float2 e23 = __fadd2_rn(make_float2(dp2, dp3), make_float2(-d4.z, -d4.w));
+          const float2 s01 = __fmul2_rn(make_float2(p[g * 32 + c], p[g * 32 + c + 1]), e01);
+          const float2 s23 = __fmul2_rn(make_float2(p[g * 32 + c + 2], p[g * 32 + c + 3]), e23);
+          out[(c >> 1)] = pack2<BF16>(s01.x, s01.y);
+          out[(c >> 1) + 1] = pack2<BF16>(s23.x, s23.y);
         }
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -378,7 +412,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     for (int which = 0; which < 2; ++which) {
       uint8_t* stage = which == 0 ? sV : sK;
       const uint32_t tm_src = which == 0 ? TM_DV : TM_DK;
-      const float mul = which == 0 ? 1.f : a.scale;
+      const float mul = which == 0 ? (DROPOUT ? a.inv_keep : 1.f) : a.scale;   // a.scale already carries 1/(1-p)
       constexpr int COLS = D / 2;                          // columns per thread (this warp's half)
 #pragma unroll
       for (int cb = 0; cb < COLS / 32; ++cb) {
@@ -421,22 +455,22 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
 template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
 static cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
-                                const CUtensorMap& tdk, const CUtensorMap& tdv, const BwdArgs& a, const TensorView& dk,
+                                const CUtensorMap& tdk, const CUtensorMap& tdv, const CUtensorMap& tdq, const BwdArgs& a, const TensorView& dk,
                                 const TensorView& dv, cudaStream_t stream) {
   auto kern = fasn_bwd_kernel<D, BF16, CAUSAL, DROPOUT>;
   constexpr int smem = BwdCfg<D>::SMEM_BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   dim3 grid((a.Skv + 127) / 128, a.B * a.H, 1);
-  kern<<<grid, kBwdThreads, smem, stream>>>(tq, tk, tv, tdo, tdk, tdv, a, dk, dv);
+  kern<<<grid, kBwdThreads, smem, stream>>>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv);
   return cudaGetLastError();
 }
 
 cudaError_t launch_bwd(int head_dim, bool bf16, bool causal, bool dropout, const CUtensorMap& tq, const CUtensorMap& tk,
                        const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
-                       const BwdArgs& a, const TensorView& dk, const TensorView& dv, cudaStream_t stream) {
+                       const CUtensorMap& tdq, const BwdArgs& a, const TensorView& dk, const TensorView& dv, cudaStream_t stream) {
 #define FASN_BWD_CASE(D_, BF_, C_, DR_) \
-  if (head_dim == D_ && bf16 == BF_ && causal == C_ && dropout == DR_) return launch_bwd_t<D_, BF_, C_, DR_>(tq, tk, tv, tdo, tdk, tdv, a, dk, dv, stream);
+  if (head_dim == D_ && bf16 == BF_ && causal == C_ && dropout == DR_) return launch_bwd_t<D_, BF_, C_, DR_>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv, stream);
   FASN_BWD_CASE(64, false, false, false) FASN_BWD_CASE(64, false, false, true)
   FASN_BWD_CASE(64, false, true, false)  FASN_BWD_CASE(64, false, true, true)
   FASN_BWD_CASE(64, true, false, false)  FASN_BWD_CASE(64, true, false, true)

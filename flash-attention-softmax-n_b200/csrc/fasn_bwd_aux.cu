@@ -45,7 +45,7 @@ fasn_bwd_prep_kernel(TensorView o, TensorView dout, BwdArgs a) {
   }
   if (lane == 0) {
     float* ws = const_cast<float*>(a.delta);
-    ws[(long long)bh * a.Sqp + row] = acc;
+    ws[(long long)bh * a.Sqp + row] = acc * a.keep_prob;    // (1-p) delta: see the dS' formulation in fasn_bwd.cu
     // second half of the workspace: LSE_n in the log2 domain, +inf on padding rows (=> P = 0 there)
     ws[(long long)a.B * a.H * a.Sqp + (long long)bh * a.Sqp + row] =
         (row < a.Sq) ? a.lse[(long long)bh * a.Sq + row] * kLog2e : INFINITY;

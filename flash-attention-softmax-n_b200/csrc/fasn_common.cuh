@@ -37,7 +37,7 @@ struct FwdArgs {
 struct BwdArgs {
   int B, H, Hkv, Sq, Skv;
   int causal_off;
-  float scale;            // logit scale (natural units)
+  float scale;            // logit scale / (1-p): multiplies dQ and dK (dS is computed without the dropout factor)
   float scale_log2;       // scale * log2(e)
   const float* lse;       // (B,H,Sq) natural log
   const float* delta;     // workspace: [0] delta (B,H,Sqp), [1] LSE_n * log2e (B,H,Sqp), written by the prep kernel
@@ -45,7 +45,8 @@ struct BwdArgs {
   int Sqp;                // Sq rounded up to 128
   AuxView mask, bias;
   uint32_t drop_thr;
-  float inv_keep;
+  float inv_keep;         // 1/(1-p)
+  float keep_prob;        // 1-p
   PhiloxKey key;
   uint32_t bh_offset;
 };
@@ -58,7 +59,8 @@ cudaError_t launch_bwd_prep(int head_dim, bool bf16, const TensorView& o, const 
                             cudaStream_t stream);
 cudaError_t launch_bwd(int head_dim, bool bf16, bool causal, bool dropout, const CUtensorMap& tq, const CUtensorMap& tk,
                        const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
-                       const BwdArgs& a, const TensorView& dk, const TensorView& dv, cudaStream_t stream);
+                       const CUtensorMap& tdq_accum, const BwdArgs& a, const TensorView& dk, const TensorView& dv,
+                       cudaStream_t stream);
 cudaError_t launch_bwd_finish(int head_dim, bool bf16, const TensorView& dq, const BwdArgs& a, cudaStream_t stream);
 
 cudaError_t launch_dropout_mask(uint8_t* out, int B, int H, int Sq, int Skv, uint32_t thr, PhiloxKey key,

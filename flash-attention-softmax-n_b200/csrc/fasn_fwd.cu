@@ -61,6 +61,11 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (CAUSAL) kv_end = min(a.Skv, min(q0 + 256, a.Sq) + a.causal_off);
   kv_end = max(kv_end, 0);
   const int n_tiles = (kv_end + 127) >> 7;
+  // per Q tile: tile 0 usually needs one K/V tile less than tile 1 under a causal mask; tile 1 is skipped
+  // entirely when all of its rows lie beyond Sq
+  int n_tiles0 = n_tiles;
+  if (CAUSAL) n_tiles0 = (max(min(a.Skv, min(q0 + 128, a.Sq) + a.causal_off), 0) + 127) >> 7;
+  const int n_tiles1 = (q0 + 128 < a.Sq) ? n_tiles : 0;
 
   if (n_tiles == 0) {
     // No key is visible to any row of this block: softmax_n gives exactly 0 (n > 0), defined 0 for n == 0.
@@ -158,14 +163,11 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         };
         mbar_wait(&q_full[0], 0);
+        mbar_wait(&q_full[1], 0);
         mbar_wait(&k_full[0], 0);
         tc_fence_after();
-        issue_qk(0, 0);
-        tc_commit(&s_full[0]);
-        mbar_wait(&q_full[1], 0);
-        tc_fence_after();
-        issue_qk(1, 0);
-        tc_commit(&s_full[1]);
+        if (n_tiles0 > 0) { issue_qk(0, 0); tc_commit(&s_full[0]); }
+        if (n_tiles1 > 0) { issue_qk(1, 0); tc_commit(&s_full[1]); }
         tc_commit(&k_empty[0]);
         for (int j = 0; j < n_tiles; ++j) {
           const int s = j % NS;
@@ -174,26 +176,23 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const uint32_t ph1 = ((j + 1) / NS) & 1;
           const bool more = (j + 1 < n_tiles);
           mbar_wait(&v_full[s], ph);
-          mbar_wait(&p_full[0], j & 1);
-          tc_fence_after();
-          issue_pv(0, s, j > 0);
-          tc_commit(&o_full[0]);
-          if (more) {
-            mbar_wait(&k_full[s1], ph1);
+          if (more) mbar_wait(&k_full[s1], ph1);
+          if (j < n_tiles0) {
+            mbar_wait(&p_full[0], j & 1);
             tc_fence_after();
-            issue_qk(0, s1);
-            tc_commit(&s_full[0]);
+            issue_pv(0, s, j > 0);
+            tc_commit(&o_full[0]);
+            if (j + 1 < n_tiles0) { issue_qk(0, s1); tc_commit(&s_full[0]); }
           }
-          mbar_wait(&p_full[1], j & 1);
-          tc_fence_after();
-          issue_pv(1, s, j > 0);
-          tc_commit(&o_full[1]);
+          if (j < n_tiles1) {
+            mbar_wait(&p_full[1], j & 1);
+            tc_fence_after();
+            issue_pv(1, s, j > 0);
+            tc_commit(&o_full[1]);
+            if (j + 1 < n_tiles1) { issue_qk(1, s1); tc_commit(&s_full[1]); }
+          }
           tc_commit(&v_empty[s]);
-          if (more) {
-            issue_qk(1, s1);
-            tc_commit(&s_full[1]);
-            tc_commit(&k_empty[s1]);
-          }
+          if (more) tc_commit(&k_empty[s1]);
         }
       }
     }
@@ -218,11 +217,23 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                                       : nullptr;
     const uint32_t bh_global = a.bh_offset + bh;
 
+    const int n_t = (t == 0) ? n_tiles0 : n_tiles1;      // K/V tiles this Q tile needs
+    // Fast path: the logit scale is folded into the exponent FFMA (p = 2^(s*c - m)) and the running max is taken on
+    // the raw scores (valid for c > 0).  Generic path (mask / bias / non-positive scale): scores are scaled first.
+    const bool generic = has_aux || !(a.scale_log2 > 0.f);
+    const float cmul = generic ? 1.f : a.scale_log2;
+    const float2 cmul2 = make_float2(cmul, cmul);
+
     float m = (a.softmax_n > 0.f) ? 0.f : -INFINITY;   // running reference max (log2 domain)
     float l = a.softmax_n;                             // running sum, starts at n (the virtual zero-logit key)
 
-    for (int j = 0; j < n_tiles; ++j) {
+    for (int j = 0; j < n_t; ++j) {
       const int j0 = j * 128;
+      uint32_t kw[4];
+      if constexpr (DROPOUT) {   // independent of S: issue before waiting for the tensor core
+#pragma unroll
+        for (int i = 0; i < 4; ++i) kw[i] = dropout_keep_word(a.key, bh_global, (uint32_t)row, (uint32_t)(j0 >> 5) + i, a.drop_thr);
+      }
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       float s[128];
@@ -234,15 +245,17 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld_x32(tS + 96, sr + 96);
         tmem_wait_ld();
       }
+      if (generic) {
 #pragma unroll
-      for (int c = 0; c < 128; ++c) s[c] *= a.scale_log2;
-      if (has_aux) {
+        for (int c = 0; c < 128; ++c) s[c] *= a.scale_log2;
+        if (has_aux) {
 #pragma unroll
-        for (int c = 0; c < 128; ++c) {
-          const int col = j0 + c;
-          if (col < a.Skv) {
-            if (brow) s[c] = fmaf(cvt16_to_f32<BF16>(brow[col]), kLog2e, s[c]);
-            if (mrow && mrow[col] == 0) s[c] = -INFINITY;
+          for (int c = 0; c < 128; ++c) {
+            const int col = j0 + c;
+            if (col < a.Skv) {
+              if (brow) s[c] = fmaf(cvt16_to_f32<BF16>(brow[col]), kLog2e, s[c]);
+              if (mrow && mrow[col] == 0) s[c] = -INFINITY;
+            }
           }
         }
       }
@@ -253,10 +266,12 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
-      for (int c = 4; c < 128; c += 4) {
-        mx0 = fmaxf(mx0, s[c]); mx1 = fmaxf(mx1, s[c + 1]); mx2 = fmaxf(mx2, s[c + 2]); mx3 = fmaxf(mx3, s[c + 3]);
+      for (int c = 4; c < 124; c += 8) {
+        mx0 = fmax3(mx0, s[c], s[c + 1]); mx1 = fmax3(mx1, s[c + 2], s[c + 3]);
+        mx2 = fmax3(mx2, s[c + 4], s[c + 5]); mx3 = fmax3(mx3, s[c + 6], s[c + 7]);
       }
-      const float tmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      mx0 = fmax3(mx0, s[124], s[125]); mx1 = fmax3(mx1, s[126], s[127]);
+      const float tmax = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * cmul;
       const bool upd = tmax > m + kRescaleThreshold;
       float alpha = 1.f;
       if (upd) {
@@ -279,17 +294,16 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
       const float m_use = (m == -INFINITY) ? 0.f : m;
-      uint32_t kw[4];
-      if constexpr (DROPOUT) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) kw[i] = dropout_keep_word(a.key, bh_global, (uint32_t)row, (uint32_t)(j0 >> 5) + i, a.drop_thr);
-      }
+      const float2 negm2 = make_float2(-m_use, -m_use);
       uint32_t pr[64];
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      float2 l01 = make_float2(0.f, 0.f), l23 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 128; c += 4) {
-        float p0 = ex2(s[c] - m_use), p1 = ex2(s[c + 1] - m_use), p2 = ex2(s[c + 2] - m_use), p3 = ex2(s[c + 3] - m_use);
-        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+        const float2 a01 = __ffma2_rn(make_float2(s[c], s[c + 1]), cmul2, negm2);
+        const float2 a23 = __ffma2_rn(make_float2(s[c + 2], s[c + 3]), cmul2, negm2);
+        float p0 = ex2(a01.x), p1 = ex2(a01.y), p2 = ex2(a23.x), p3 = ex2(a23.y);
+        l01 = __fadd2_rn(l01, make_float2(p0, p1));
+        l23 = __fadd2_rn(l23, make_float2(p2, p3));
         if constexpr (DROPOUT) {
           const uint32_t w = kw[c >> 5];
           p0 = (w & (1u << ((c + 0) & 31))) ? p0 : 0.f;
@@ -300,7 +314,7 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         pr[c >> 1] = pack2<BF16>(p0, p1);
         pr[(c >> 1) + 1] = pack2<BF16>(p2, p3);
       }
-      l += (l0 + l1) + (l2 + l3);
+      l += (l01.x + l01.y) + (l23.x + l23.y);
       tmem_st_x32(tS, pr);
       tmem_st_x32(tS + 32, pr + 32);
       tmem_wait_st();
@@ -309,15 +323,24 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
 
     // ------------------------------------------------------------------ epilogue
-    mbar_wait(&o_full[t], (n_tiles - 1) & 1);
-    tc_fence_after();
-    const float inv = (l > 0.f) ? (DROPOUT ? a.inv_keep : 1.f) / l : 0.f;
+    if (n_t > 0) {
+      mbar_wait(&o_full[t], (n_t - 1) & 1);
+      tc_fence_after();
+    } else {
+      mbar_wait(&q_full[t], 0);   // the Q_t load must have landed before its buffer is reused for the (zero) output
+    }
+    const float inv = (l > 0.f && n_t > 0) ? (DROPOUT ? a.inv_keep : 1.f) / l : 0.f;
     uint8_t* sO = sQ + t * TILE_BYTES;    // Q_t is dead: every MMA that read it completed before o_full fired
 #pragma unroll
     for (int cb = 0; cb < D / 32; ++cb) {
       uint32_t o[32];
-      tmem_ld_x32(tO + cb * 32, o);
-      tmem_wait_ld();
+      if (n_t > 0) {
+        tmem_ld_x32(tO + cb * 32, o);
+        tmem_wait_ld();
+      } else {                        // no visible key for this Q tile: the accumulator was never written
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0u;
+      }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {   // 4 x 16-byte chunks (8 elements each)
         uint4 v;

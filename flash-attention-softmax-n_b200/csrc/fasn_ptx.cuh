@@ -43,6 +43,26 @@ FASN_DEVICE float lg2(float x) {
   return y;
 }
 
+// 3-input max (one FMNMX3 on sm_100)
+FASN_DEVICE float fmax3(float a, float b, float c) {
+  float y;
+  asm("max.f32 %0, %1, %2, %3;\n" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
+
+// Transpose a 32x32 bit matrix held one row per lane: afterwards bit L of lane j's word = bit j of lane L's
+// input word.  Five butterfly steps (shfl.bfly + select) instead of 32 broadcasts.
+FASN_DEVICE uint32_t warp_transpose_bits(uint32_t x, int lane) {
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int k = 16 >> i;
+    const uint32_t m = (k == 16) ? 0x0000FFFFu : (k == 8) ? 0x00FF00FFu : (k == 4) ? 0x0F0F0F0Fu : (k == 2) ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, k);
+    x = (lane & k) ? ((x & ~m) | ((y >> k) & m)) : ((x & m) | ((y & m) << k));
+  }
+  return x;
+}
+
 // pack two fp32 into one 32-bit word of two 16-bit floats; `lo` lands in bits [0,16)
 template <bool BF16> FASN_DEVICE uint32_t pack2(float lo, float hi) {
   uint32_t r;
@@ -81,10 +101,10 @@ FASN_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware instead of polling
       : "memory");
   return ok != 0;
 }
