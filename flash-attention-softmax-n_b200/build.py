@@ -38,8 +38,14 @@ def _newest_dep() -> float:
     return t
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every translation unit (in parallel) and link the shared library; returns its path."""
+def build(force: bool = False, verbose: bool = False, timeline: bool = False) -> str:
+    """Compile every translation unit (in parallel) and link the shared library; returns its path.
+    `timeline=True` builds the instrumented variant libfasn_timeline.so (-DFASN_TIMELINE, scripts/timeline.py)."""
+    global OBJ, LIB
+    flags = list(NVCC_FLAGS)
+    if timeline:
+        OBJ, LIB = os.path.join(HERE, "build_timeline"), os.path.join(HERE, "flash_attention_softmax_n", "libfasn_timeline.so")
+        flags.append("-DFASN_TIMELINE")
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_dep():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
@@ -47,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -67,4 +73,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, timeline="--timeline" in sys.argv))

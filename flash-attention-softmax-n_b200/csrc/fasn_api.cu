@@ -160,6 +160,14 @@ fasn::PhiloxKey philox_key(uint64_t seed, uint64_t offset) {
 
 }  // namespace
 
+#ifdef FASN_TIMELINE
+unsigned long long* g_fasn_timeline = nullptr;
+unsigned int g_fasn_timeline_xy[2] = {0, 0};
+extern "C" void fasn_set_timeline(unsigned long long* buf, unsigned int x, unsigned int y) {
+  g_fasn_timeline = buf; g_fasn_timeline_xy[0] = x; g_fasn_timeline_xy[1] = y;
+}
+#endif
+
 extern "C" {
 
 int fasn_version(void) { return FASN_ABI_VERSION; }
@@ -242,6 +250,12 @@ int fasn_bwd(const FasnParams* p) {
   a.inv_keep = 1.0f / (1.0f - p->dropout_p);
   a.key = philox_key(p->philox_seed, p->philox_offset);
   a.bh_offset = (uint32_t)p->bh_offset;
+#ifdef FASN_TIMELINE
+  {
+    extern unsigned long long* g_fasn_timeline; extern unsigned int g_fasn_timeline_xy[2];
+    a.dbg = g_fasn_timeline; a.dbg_x = g_fasn_timeline_xy[0]; a.dbg_y = g_fasn_timeline_xy[1];
+  }
+#endif
   cudaStream_t st = (cudaStream_t)p->stream;
   cudaError_t e = fasn::launch_bwd_prep(D, bf16, tensor_view(p->o), tensor_view(p->dout), a, st);
   if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd prep launch");

@@ -29,6 +29,18 @@ namespace fasn {
 
 namespace {
 
+// Optional phase timeline (compile with -DFASN_TIMELINE): one CTA records clock64() at its pipeline events into
+// BwdArgs.dbg, [role][slot] = (tag << 48) | clock.  Used by scripts/timeline.py; compiled out of the product build.
+#ifdef FASN_TIMELINE
+#define TL_DECL(role) unsigned long long* tl_p = (a.dbg && blockIdx.x == a.dbg_x && blockIdx.y == a.dbg_y) ? a.dbg + (role) * 2048 : nullptr; int tl_i = 0;
+#define TL_ONLY(cond) do { if (!(cond)) tl_p = nullptr; } while (0)
+#define TL(tag) do { if (tl_p && tl_i < 2048) tl_p[tl_i++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
+#else
+#define TL_DECL(role)
+#define TL_ONLY(cond)
+#define TL(tag)
+#endif
+
 constexpr int kBwdThreads = 512;
 
 template <int D> struct BwdCfg {
@@ -186,9 +198,11 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           umma_ss(tmem_base + tm_dst, umma_smem_desc(a_u + off, 16, 1024), umma_smem_desc(b_u + off, 16, 1024), idesc_kk, kb > 0 ? 1u : 0u);
         }
       };
+      TL_DECL(0)
       mbar_wait(kv_full, 0);
       mbar_wait(&q_full[0], 0);
       tc_fence_after();
+      TL(1);
       issue_kmajor(TM_S, sK_u, sQ_u);
       tc_commit(s_full);
       mbar_wait(do_full, 0);
@@ -203,6 +217,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // dV += P^T dO_i
         mbar_wait(p_full, it & 1);
         tc_fence_after();
+        TL(2);
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb)
           umma_ts(tmem_base + TM_DV, tmem_base + TM_S + (kb >> 2) * 64 + (kb & 3) * 8,
@@ -212,12 +227,19 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (more) {
           mbar_wait(&q_full[s1], ph1);
           tc_fence_after();
+          TL(3);
           issue_kmajor(TM_S, sK_u, sQ_u + s1 * TILE_BYTES);
           tc_commit(s_full);
         }
-        // dK += dS^T Q_i ;  dQ_i = dS K
+        // dQ_i = dS K first (its consumers, the reducer warps, then drain TMEM while dK executes) ;  dK += dS^T Q_i
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
+        TL(4);
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb)
+          umma_ss(tmem_base + TM_DQ, umma_smem_desc(sDS_u + kb * 2048, BLK_BYTES, 1024), umma_smem_desc(sK_u + kb * 2048, BLK_BYTES, 1024),
+                  idesc_dq, kb > 0 ? 1u : 0u);
+        tc_commit(dq_full);
 #pragma unroll
         for (int kb = 0; kb < 8; ++kb) {
           const uint32_t off = (kb >> 2) * BLK_BYTES + (kb & 3) * 32;
@@ -226,17 +248,14 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         tc_commit(&q_empty[s]);      // Q_i, LSE2_i and delta_i stay valid until the compute warps are done with tile i
                                      // (ds_full above) and the MMAs that read Q_i have completed
-#pragma unroll
-        for (int kb = 0; kb < 8; ++kb)
-          umma_ss(tmem_base + TM_DQ, umma_smem_desc(sDS_u + kb * 2048, BLK_BYTES, 1024), umma_smem_desc(sK_u + kb * 2048, BLK_BYTES, 1024),
-                  idesc_dq, kb > 0 ? 1u : 0u);
-        tc_commit(dq_full);
         tc_commit(ds_empty);
         // dP^T of the next tile reuses the dQ columns: wait until the reducers have drained dQ_i
         if (more) {
           mbar_wait(do_full, (it + 1) & 1);
+          TL(5);
           mbar_wait(dq_empty, it & 1);
           tc_fence_after();
+          TL(6);
           issue_kmajor(TM_DP, sV_u, sDO_u);
           tc_commit(dp_full);
         }
@@ -251,26 +270,33 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int r = (warp & 3) * 32 + lane;                 // query row inside the tile
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     constexpr int NCH = D / 32;                           // 32-column chunks per dQ tile
+    TL_DECL(3)
+    TL_ONLY(threadIdx.x == 256);
     for (int it = 0; it < n_iter; ++it) {
       const int qi0 = (i_start + it) * 128;
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
+      TL(30);
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem_base + lane_off + TM_DQ + ch * 32, v);
+      for (int hb = 0; hb < NCH / 2; ++hb) {                // 64 columns (both staging chunks) per round
+        uint32_t v[64];
+        tmem_ld_x32(tmem_base + lane_off + TM_DQ + hb * 64, v);
+        tmem_ld_x32(tmem_base + lane_off + TM_DQ + hb * 64 + 32, v + 32);
         tmem_wait_ld();
-        if (ch == NCH - 1) { tc_fence_before(); mbar_arrive(dq_empty); }    // dQ columns may be overwritten by dP^T now
-        uint8_t* stage = sDQ + (ch & 1) * Cfg::DQ_STAGE_BYTES;
-        if (threadIdx.x == 256) tma_store_wait_read<1>();                   // the reduce issued two chunks ago has read this buffer
+        if (hb == NCH / 2 - 1) { tc_fence_before(); mbar_arrive(dq_empty); TL(31); }   // dQ columns may be overwritten by dP^T now
+        if (threadIdx.x == 256) tma_store_wait_read<0>();   // the previous round's reduces have read both staging chunks
         named_bar_sync(2, 128);
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<uint4*>(stage + r * 128 + ((g ^ (r & 7)) << 4)) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(sDQ + ch * Cfg::DQ_STAGE_BYTES + r * 128 + ((g ^ (r & 7)) << 4)) =
+                make_uint4(v[ch * 32 + g * 4], v[ch * 32 + g * 4 + 1], v[ch * 32 + g * 4 + 2], v[ch * 32 + g * 4 + 3]);
         fence_proxy_async_smem();
         named_bar_sync(3, 128);
         if (threadIdx.x == 256) {
-          tma_reduce_add_4d(&tm_dq, stage, ch * 32, qi0, bh, 0);
+          tma_reduce_add_4d(&tm_dq, sDQ, hb * 64, qi0, bh, 0);
+          tma_reduce_add_4d(&tm_dq, sDQ + Cfg::DQ_STAGE_BYTES, hb * 64 + 32, qi0, bh, 0);
           tma_store_commit();
         }
       }
@@ -293,6 +319,8 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t kvw = (uint32_t)(kv_row >> 5);          // identical for the 32 lanes of this warp
 
     const bool kv_tail = (k0 + 128 > a.Skv);               // this K/V tile has rows beyond Skv
+    TL_DECL(1 + half)
+    TL_ONLY(threadIdx.x == 0 || threadIdx.x == 128);
     const float2 c2 = make_float2(a.scale_log2, a.scale_log2);
 
     for (int it = 0; it < n_iter; ++it) {
@@ -309,9 +337,11 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         keep1 = warp_transpose_bits(dropout_keep_word(a.key, bh_global, (uint32_t)(qc0 + 32 + lane), kvw, a.drop_thr), lane);
       }
       // ---- P^T = 2^(S^T c - LSE2)
+      TL(10);
       mbar_wait(&q_full[s], ph);          // LSE2 and delta of this tile have landed (same barrier as Q_i)
       mbar_wait(s_full, it & 1);
       tc_fence_after();
+      TL(11);
       float p[64];
       {
         uint32_t* pr = reinterpret_cast<uint32_t*>(p);
@@ -363,10 +393,13 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(p_full);
+      TL(12);
       // ---- dS'^T = P^T o (Z dP^T - (1-p) delta)      (dS = dS' / (1-p); the factor is folded into the dK / dQ scales)
       mbar_wait(dp_full, it & 1);
       tc_fence_after();
+      TL(13);
       mbar_wait(ds_empty, (it & 1) ^ 1);  // MMAs of the previous iteration no longer read the dS^T tile
+      TL(14);
       const float* del_s = sDelta + s * 128 + half * 64;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -402,6 +435,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(ds_full);
+      TL(15);
     }
 
     // ------------------------------------------------------------------ dK, dV epilogue

@@ -49,6 +49,8 @@ struct BwdArgs {
   float keep_prob;        // 1-p
   PhiloxKey key;
   uint32_t bh_offset;
+  unsigned long long* dbg;   // FASN_TIMELINE builds only: phase timeline buffer (see fasn_bwd.cu)
+  unsigned int dbg_x, dbg_y;
 };
 
 // launchers implemented in the kernel translation units
