@@ -323,19 +323,25 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     TL_ONLY(threadIdx.x == 0 || threadIdx.x == 128);
     const float2 c2 = make_float2(a.scale_log2, a.scale_log2);
 
+    // Dropout keep bits: lane L generates the 32-key keep words of query rows qc0+L and qc0+32+L; a 32x32 bit
+    // transpose across the warp then hands every lane (= kv row) its own bit of all 64 query columns.
+    uint32_t keep_next0 = 0xFFFFFFFFu, keep_next1 = 0xFFFFFFFFu;
+    auto make_keep = [&](int qc0n) {
+      if constexpr (DROPOUT) {
+        keep_next0 = warp_transpose_bits(dropout_keep_word(a.key, bh_global, (uint32_t)(qc0n + lane), kvw, a.drop_thr), lane);
+        keep_next1 = warp_transpose_bits(dropout_keep_word(a.key, bh_global, (uint32_t)(qc0n + 32 + lane), kvw, a.drop_thr), lane);
+      }
+    };
+    make_keep(i_start * 128 + half * 64);
+
     for (int it = 0; it < n_iter; ++it) {
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       const int qi0 = (i_start + it) * 128;
       const int qc0 = qi0 + half * 64;                     // first query column of this thread
-      // keep0 / keep1: bit c = keep decision for (query qc0 + c [+32], this thread's kv row)
-      uint32_t keep0 = 0xFFFFFFFFu, keep1 = 0xFFFFFFFFu;
-      if constexpr (DROPOUT) {
-        // lane L generates the 32-key keep words of query rows qc0+L and qc0+32+L; a 32x32 bit transpose across the
-        // warp then hands every lane (= kv row) its own bit of all 64 query columns
-        keep0 = warp_transpose_bits(dropout_keep_word(a.key, bh_global, (uint32_t)(qc0 + lane), kvw, a.drop_thr), lane);
-        keep1 = warp_transpose_bits(dropout_keep_word(a.key, bh_global, (uint32_t)(qc0 + 32 + lane), kvw, a.drop_thr), lane);
-      }
+      // keep0 / keep1: bit c = keep decision for (query qc0 + c [+32], this thread's kv row); generated one
+      // iteration ahead (below), in the slot where this warp would otherwise wait for dP^T
+      const uint32_t keep0 = keep_next0, keep1 = keep_next1;
       // ---- P^T = 2^(S^T c - LSE2)
       TL(10);
       mbar_wait(&q_full[s], ph);          // LSE2 and delta of this tile have landed (same barrier as Q_i)
@@ -394,6 +400,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       mbar_arrive(p_full);
       TL(12);
+      if (it + 1 < n_iter) make_keep(qc0 + 128);            // next tile's keep bits, while dP^T is still in flight
       // ---- dS'^T = P^T o (Z dP^T - (1-p) delta)      (dS = dS' / (1-p); the factor is folded into the dK / dQ scales)
       mbar_wait(dp_full, it & 1);
       tc_fence_after();
