@@ -38,6 +38,19 @@ def _newest_dep() -> float:
     return t
 
 
+def build_variant(name: str, extra_flags) -> str:
+    """Experimental variant libfasn_<name>.so with extra nvcc flags (tuning sweeps; select it with FASN_LIBRARY)."""
+    global OBJ, LIB
+    old = (OBJ, LIB, list(NVCC_FLAGS))
+    try:
+        OBJ, LIB = os.path.join(HERE, "build_" + name), os.path.join(HERE, "flash_attention_softmax_n", f"libfasn_{name}.so")
+        NVCC_FLAGS.extend(extra_flags)
+        return build(force=True)
+    finally:
+        OBJ, LIB = old[0], old[1]
+        NVCC_FLAGS[:] = old[2]
+
+
 def build(force: bool = False, verbose: bool = False, timeline: bool = False) -> str:
     """Compile every translation unit (in parallel) and link the shared library; returns its path.
     `timeline=True` builds the instrumented variant libfasn_timeline.so (-DFASN_TIMELINE, scripts/timeline.py)."""

@@ -163,6 +163,11 @@ fasn::PhiloxKey philox_key(uint64_t seed, uint64_t offset) {
 #ifdef FASN_TIMELINE
 unsigned long long* g_fasn_timeline = nullptr;
 unsigned int g_fasn_timeline_xy[2] = {0, 0};
+unsigned long long* g_fasn_timeline_fwd = nullptr;
+unsigned int g_fasn_timeline_fwd_xy[2] = {0, 0};
+extern "C" void fasn_set_timeline_fwd(unsigned long long* buf, unsigned int x, unsigned int y) {
+  g_fasn_timeline_fwd = buf; g_fasn_timeline_fwd_xy[0] = x; g_fasn_timeline_fwd_xy[1] = y;
+}
 extern "C" void fasn_set_timeline(unsigned long long* buf, unsigned int x, unsigned int y) {
   g_fasn_timeline = buf; g_fasn_timeline_xy[0] = x; g_fasn_timeline_xy[1] = y;
 }
@@ -199,6 +204,12 @@ int fasn_fwd(const FasnParams* p) {
   a.inv_keep = 1.0f / (1.0f - p->dropout_p);
   a.key = philox_key(p->philox_seed, p->philox_offset);
   a.bh_offset = (uint32_t)p->bh_offset;
+#ifdef FASN_TIMELINE
+  {
+    extern unsigned long long* g_fasn_timeline_fwd; extern unsigned int g_fasn_timeline_fwd_xy[2];
+    a.dbg = g_fasn_timeline_fwd; a.dbg_x = g_fasn_timeline_fwd_xy[0]; a.dbg_y = g_fasn_timeline_fwd_xy[1];
+  }
+#endif
   cudaError_t e;
   {
     ScopedEvents prof(g_prof.fwd, (cudaStream_t)p->stream);

@@ -21,7 +21,7 @@
 //   warps 0-7   compute: warp w owns TMEM lanes 32(w%4).. (kv rows) and q-columns 64(w/4)..64(w/4)+63
 //   warps 8-11  dQ reducers: TMEM -> registers -> fp32 staging in smem -> TMA reduce-add
 //   warp 12     TMA producer (K,V once; Q_i + LSE2 + delta through a 2-deep ring, dO_i single-buffered)
-//   warp 13     MMA issuer (one thread)        warp 14  TMEM allocator        warp 15  idle
+//   warp 13     MMA issuer (one elected lane)  warp 14  TMEM allocator        warp 15  idle
 #include "fasn_common.cuh"
 #include "fasn_ptx.cuh"
 
@@ -184,31 +184,42 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int db = 0; db < DB; ++db) tma_load_4d(sDO + db * BLK_BYTES, &tm_do, do_full, db * 64, qi0, h, b);
       }
-    } else if (warp == 13 && lane == 0) {
+    } else if (warp == 13) {
       // ---------------------------------------------------------------- MMA issuer
+      // The whole warp walks the schedule (operands stay in uniform registers), one elected lane issues; descriptors
+      // are base words computed once plus compile-time offsets, so a tcgen05.mma costs a few issue slots.
       constexpr uint32_t idesc_kk = umma_idesc(BF16, 128, 128, false, false);   // S^T, dP^T
       constexpr uint32_t idesc_dv = umma_idesc(BF16, 128, D, false, true);      // A in TMEM, B MN-major
       constexpr uint32_t idesc_dk = umma_idesc(BF16, 128, D, false, true);      // A K-major smem, B MN-major
       constexpr uint32_t idesc_dq = umma_idesc(BF16, 128, D, true, true);       // A, B MN-major
-      const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV), sQ_u = smem_u32(sQ), sDO_u = smem_u32(sDO), sDS_u = smem_u32(sDS);
-      auto issue_kmajor = [&](uint32_t tm_dst, uint32_t a_u, uint32_t b_u) {    // D[128x128] = A B^T over K = head dim
+      constexpr uint32_t hi_desc = umma_desc_hi(1024);
+      constexpr uint32_t TILE16 = TILE_BYTES >> 4;
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      // K-major views (LBO unused) and MN-major views (LBO = next 64-wide block) of the operand tiles
+      const uint32_t k_km = umma_desc_lo(smem_u32(sK), 16), v_km = umma_desc_lo(smem_u32(sV), 16);
+      const uint32_t q_km = umma_desc_lo(smem_u32(sQ), 16), do_km = umma_desc_lo(smem_u32(sDO), 16);
+      const uint32_t ds_km = umma_desc_lo(smem_u32(sDS), 16);
+      const uint32_t k_mn = umma_desc_lo(smem_u32(sK), BLK_BYTES), q_mn = umma_desc_lo(smem_u32(sQ), BLK_BYTES);
+      const uint32_t do_mn = umma_desc_lo(smem_u32(sDO), BLK_BYTES), ds_mn = umma_desc_lo(smem_u32(sDS), BLK_BYTES);
+      auto issue_kmajor = [&](uint32_t tm_dst, uint32_t a_lo, uint32_t b_lo) {  // D[128x128] = A B^T over K = head dim
 #pragma unroll
         for (int kb = 0; kb < D / 16; ++kb) {
-          const uint32_t off = (kb >> 2) * BLK_BYTES + (kb & 3) * 32;
-          umma_ss(tmem_base + tm_dst, umma_smem_desc(a_u + off, 16, 1024), umma_smem_desc(b_u + off, 16, 1024), idesc_kk, kb > 0 ? 1u : 0u);
+          const uint32_t off = ((kb >> 2) * BLK_BYTES + (kb & 3) * 32) >> 4;
+          umma_ss(tm + tm_dst, umma_desc_join(a_lo + off, hi_desc), umma_desc_join(b_lo + off, hi_desc), idesc_kk, kb > 0 ? 1u : 0u);
         }
       };
       TL_DECL(0)
+      TL_ONLY(lane == 0);
       mbar_wait(kv_full, 0);
       mbar_wait(&q_full[0], 0);
       tc_fence_after();
       TL(1);
-      issue_kmajor(TM_S, sK_u, sQ_u);
-      tc_commit(s_full);
+      if (elect_one()) { issue_kmajor(TM_S, k_km, q_km); tc_commit(s_full); }
+      __syncwarp();
       mbar_wait(do_full, 0);
       tc_fence_after();
-      issue_kmajor(TM_DP, sV_u, sDO_u);
-      tc_commit(dp_full);
+      if (elect_one()) { issue_kmajor(TM_DP, v_km, do_km); tc_commit(dp_full); }
+      __syncwarp();
       for (int it = 0; it < n_iter; ++it) {
         const int s = it & 1;
         const int s1 = s ^ 1;
@@ -218,37 +229,43 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(p_full, it & 1);
         tc_fence_after();
         TL(2);
+        if (elect_one()) {
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb)
-          umma_ts(tmem_base + TM_DV, tmem_base + TM_S + (kb >> 2) * 64 + (kb & 3) * 8,
-                  umma_smem_desc(sDO_u + kb * 2048, BLK_BYTES, 1024), idesc_dv, (it > 0 || kb > 0) ? 1u : 0u);
-        tc_commit(do_empty);         // dO_i is dead once dP^T_i (issued earlier) and dV_i have completed
+          for (int kb = 0; kb < 8; ++kb)
+            umma_ts(tm + TM_DV, tm + TM_S + (kb >> 2) * 64 + (kb & 3) * 8, umma_desc_join(do_mn + kb * (2048 >> 4), hi_desc),
+                    idesc_dv, (it > 0 || kb > 0) ? 1u : 0u);
+          tc_commit(do_empty);         // dO_i is dead once dP^T_i (issued earlier) and dV_i have completed
+        }
+        __syncwarp();
         // S^T of the next Q tile (overwrites P^T: ordered behind the dV MMAs on the tensor pipe)
         if (more) {
           mbar_wait(&q_full[s1], ph1);
           tc_fence_after();
           TL(3);
-          issue_kmajor(TM_S, sK_u, sQ_u + s1 * TILE_BYTES);
-          tc_commit(s_full);
+          if (elect_one()) { issue_kmajor(TM_S, k_km, q_km + s1 * TILE16); tc_commit(s_full); }
+          __syncwarp();
         }
         // dQ_i = dS K first (its consumers, the reducer warps, then drain TMEM while dK executes) ;  dK += dS^T Q_i
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
         TL(4);
+        if (elect_one()) {
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb)
-          umma_ss(tmem_base + TM_DQ, umma_smem_desc(sDS_u + kb * 2048, BLK_BYTES, 1024), umma_smem_desc(sK_u + kb * 2048, BLK_BYTES, 1024),
-                  idesc_dq, kb > 0 ? 1u : 0u);
-        tc_commit(dq_full);
+          for (int kb = 0; kb < 8; ++kb)
+            umma_ss(tm + TM_DQ, umma_desc_join(ds_mn + kb * (2048 >> 4), hi_desc), umma_desc_join(k_mn + kb * (2048 >> 4), hi_desc),
+                    idesc_dq, kb > 0 ? 1u : 0u);
+          tc_commit(dq_full);
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb) {
-          const uint32_t off = (kb >> 2) * BLK_BYTES + (kb & 3) * 32;
-          umma_ss(tmem_base + TM_DK, umma_smem_desc(sDS_u + off, 16, 1024),
-                  umma_smem_desc(sQ_u + s * TILE_BYTES + kb * 2048, BLK_BYTES, 1024), idesc_dk, (it > 0 || kb > 0) ? 1u : 0u);
+          for (int kb = 0; kb < 8; ++kb) {
+            const uint32_t off = ((kb >> 2) * BLK_BYTES + (kb & 3) * 32) >> 4;
+            umma_ss(tm + TM_DK, umma_desc_join(ds_km + off, hi_desc), umma_desc_join(q_mn + s * TILE16 + kb * (2048 >> 4), hi_desc),
+                    idesc_dk, (it > 0 || kb > 0) ? 1u : 0u);
+          }
+          tc_commit(&q_empty[s]);      // Q_i, LSE2_i and delta_i stay valid until the compute warps are done with tile i
+                                       // (ds_full above) and the MMAs that read Q_i have completed
+          tc_commit(ds_empty);
         }
-        tc_commit(&q_empty[s]);      // Q_i, LSE2_i and delta_i stay valid until the compute warps are done with tile i
-                                     // (ds_full above) and the MMAs that read Q_i have completed
-        tc_commit(ds_empty);
+        __syncwarp();
         // dP^T of the next tile reuses the dQ columns: wait until the reducers have drained dQ_i
         if (more) {
           mbar_wait(do_full, (it + 1) & 1);
@@ -256,11 +273,12 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(dq_empty, it & 1);
           tc_fence_after();
           TL(6);
-          issue_kmajor(TM_DP, sV_u, sDO_u);
-          tc_commit(dp_full);
+          if (elect_one()) { issue_kmajor(TM_DP, v_km, do_km); tc_commit(dp_full); }
+          __syncwarp();
         }
       }
-      tc_commit(dkv_full);
+      if (elect_one()) tc_commit(dkv_full);
+      __syncwarp();
     }
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ dQ reducers
@@ -284,6 +302,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld_x32(tmem_base + lane_off + TM_DQ + hb * 64 + 32, v + 32);
         tmem_wait_ld();
         if (hb == NCH / 2 - 1) { tc_fence_before(); mbar_arrive(dq_empty); TL(31); }   // dQ columns may be overwritten by dP^T now
+#ifndef FASN_EXP_NO_DQ
         if (threadIdx.x == 256) tma_store_wait_read<0>();   // the previous round's reduces have read both staging chunks
         named_bar_sync(2, 128);
 #pragma unroll
@@ -299,6 +318,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tma_reduce_add_4d(&tm_dq, sDQ + Cfg::DQ_STAGE_BYTES, hb * 64 + 32, qi0, bh, 0);
           tma_store_commit();
         }
+#endif
       }
     }
     if (threadIdx.x == 256) tma_store_wait_all();

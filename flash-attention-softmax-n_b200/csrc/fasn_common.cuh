@@ -32,6 +32,8 @@ struct FwdArgs {
   float inv_keep;         // 1/(1-p)
   PhiloxKey key;
   uint32_t bh_offset;
+  unsigned long long* dbg;   // FASN_TIMELINE builds only
+  unsigned int dbg_x, dbg_y;
 };
 
 struct BwdArgs {

@@ -28,8 +28,25 @@ namespace fasn {
 
 namespace {
 
+// Optional phase timeline (compile with -DFASN_TIMELINE; see fasn_bwd.cu / scripts/timeline.py)
+#ifdef FASN_TIMELINE
+#define TLF_DECL(role) unsigned long long* tl_p = (a.dbg && blockIdx.x == a.dbg_x && blockIdx.y == a.dbg_y) ? a.dbg + (role) * 2048 : nullptr; int tl_i = 0;
+#define TLF_ONLY(cond) do { if (!(cond)) tl_p = nullptr; } while (0)
+#define TLF(tag) do { if (tl_p && tl_i < 2048) tl_p[tl_i++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
+#else
+#define TLF_DECL(role)
+#define TLF_ONLY(cond)
+#define TLF(tag)
+#endif
+
 constexpr int kFwdThreads = 384;
 constexpr float kRescaleThreshold = 8.0f;   // log2 units
+// Share of the exponentials evaluated by exp2_poly_pair instead of MUFU.EX2 on unmasked tiles: in kPolyCount of
+// every kPolyPeriod groups of four elements, one of the two pairs is a polynomial (1 of 2 -> 25 %).  0 disables.
+// Measured on B200 (profiles/README.md): 25 % helps head dim 64 (+4..8 %) and the dropout kernels (+3 %), and costs
+// 2 % on the D=128 no-dropout kernel, which therefore keeps every exponential on the MUFU.
+constexpr int kPolyPeriod = 2;
+
 
 template <int D> struct FwdCfg {
   static constexpr int NS = (D == 128) ? 2 : 4;          // K/V ring depth
@@ -141,59 +158,80 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     } else if (warp == 9) {
-      // ------------------------------------------------------------------ MMA issuer (one thread)
-      if (lane == 0) {
-        constexpr uint32_t idesc_qk = umma_idesc(BF16, 128, 128, false, false);
-        constexpr uint32_t idesc_pv = umma_idesc(BF16, 128, D, false, true);
-        const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
-        auto issue_qk = [&](int t, int s) {
+      // ------------------------------------------------------------------ MMA issuer
+      // The whole warp walks the schedule (so every operand stays in uniform registers); one elected lane issues.
+      // Descriptors are base words computed once plus compile-time offsets: the issue loop is a handful of
+      // instructions per tcgen05.mma, well under the 64 cycles each 128x128x16 MMA occupies the tensor pipe.
+      constexpr uint32_t idesc_qk = umma_idesc(BF16, 128, 128, false, false);
+      constexpr uint32_t idesc_pv = umma_idesc(BF16, 128, D, false, true);
+      constexpr uint32_t hi_desc = umma_desc_hi(1024);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t q_lo = umma_desc_lo(smem_u32(sQ), 16);            // K-major: LBO unused
+      const uint32_t k_lo = umma_desc_lo(smem_u32(sK), 16);
+      const uint32_t v_lo = umma_desc_lo(smem_u32(sV), BLK_BYTES);     // MN-major: LBO = next 64-wide block of D
+      auto issue_qk = [&](int t, int s) {
+        const uint32_t a0 = q_lo + t * (TILE_BYTES >> 4), b0 = k_lo + s * (TILE_BYTES >> 4);
 #pragma unroll
-          for (int kb = 0; kb < D / 16; ++kb) {
-            const uint32_t off = (kb >> 2) * BLK_BYTES + (kb & 3) * 32;
-            umma_ss(tmem_base + t * 128, umma_smem_desc(sQ_u + t * TILE_BYTES + off, 16, 1024),
-                    umma_smem_desc(sK_u + s * TILE_BYTES + off, 16, 1024), idesc_qk, kb > 0 ? 1u : 0u);
-          }
-        };
-        auto issue_pv = [&](int t, int s, bool acc) {
+        for (int kb = 0; kb < D / 16; ++kb) {
+          const uint32_t off = ((kb >> 2) * BLK_BYTES + (kb & 3) * 32) >> 4;
+          umma_ss(tm + t * 128, umma_desc_join(a0 + off, hi_desc), umma_desc_join(b0 + off, hi_desc), idesc_qk, kb > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int t, int s, uint32_t acc) {
+        const uint32_t b0 = v_lo + s * (TILE_BYTES >> 4);
 #pragma unroll
-          for (int kb = 0; kb < 8; ++kb) {
-            umma_ts(tmem_base + 256 + t * D, tmem_base + t * 128 + kb * 8,
-                    umma_smem_desc(sV_u + s * TILE_BYTES + kb * 2048, BLK_BYTES, 1024), idesc_pv,
-                    (acc || kb > 0) ? 1u : 0u);
-          }
-        };
-        mbar_wait(&q_full[0], 0);
-        mbar_wait(&q_full[1], 0);
-        mbar_wait(&k_full[0], 0);
-        tc_fence_after();
+        for (int kb = 0; kb < 8; ++kb)
+          umma_ts(tm + 256 + t * D, tm + t * 128 + kb * 8, umma_desc_join(b0 + kb * (2048 >> 4), hi_desc), idesc_pv, kb > 0 ? 1u : acc);
+      };
+      TLF_DECL(0)
+      TLF_ONLY(lane == 0);
+      mbar_wait(&q_full[0], 0);
+      mbar_wait(&q_full[1], 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      TLF(1);
+      if (elect_one()) {
         if (n_tiles0 > 0) { issue_qk(0, 0); tc_commit(&s_full[0]); }
         if (n_tiles1 > 0) { issue_qk(1, 0); tc_commit(&s_full[1]); }
         tc_commit(&k_empty[0]);
-        for (int j = 0; j < n_tiles; ++j) {
-          const int s = j % NS;
-          const uint32_t ph = (j / NS) & 1;
-          const int s1 = (j + 1) % NS;
-          const uint32_t ph1 = ((j + 1) / NS) & 1;
-          const bool more = (j + 1 < n_tiles);
-          mbar_wait(&v_full[s], ph);
-          if (more) mbar_wait(&k_full[s1], ph1);
-          if (j < n_tiles0) {
-            mbar_wait(&p_full[0], j & 1);
-            tc_fence_after();
-            issue_pv(0, s, j > 0);
+      }
+      __syncwarp();
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % NS;
+        const uint32_t ph = (j / NS) & 1;
+        const int s1 = (j + 1) % NS;
+        const uint32_t ph1 = ((j + 1) / NS) & 1;
+        const bool more = (j + 1 < n_tiles);
+        mbar_wait(&v_full[s], ph);
+        if (more) mbar_wait(&k_full[s1], ph1);
+        if (j < n_tiles0) {
+          mbar_wait(&p_full[0], j & 1);
+          tc_fence_after();
+          TLF(2);
+          if (elect_one()) {
+            issue_pv(0, s, j > 0 ? 1u : 0u);
             tc_commit(&o_full[0]);
             if (j + 1 < n_tiles0) { issue_qk(0, s1); tc_commit(&s_full[0]); }
           }
-          if (j < n_tiles1) {
-            mbar_wait(&p_full[1], j & 1);
-            tc_fence_after();
-            issue_pv(1, s, j > 0);
+          __syncwarp();
+        }
+        if (j < n_tiles1) {
+          mbar_wait(&p_full[1], j & 1);
+          tc_fence_after();
+          TLF(3);
+          if (elect_one()) {
+            issue_pv(1, s, j > 0 ? 1u : 0u);
             tc_commit(&o_full[1]);
             if (j + 1 < n_tiles1) { issue_qk(1, s1); tc_commit(&s_full[1]); }
           }
+          __syncwarp();
+        }
+        if (elect_one()) {
           tc_commit(&v_empty[s]);
           if (more) tc_commit(&k_empty[s1]);
         }
+        __syncwarp();
+        TLF(4);
       }
     }
   } else {
@@ -227,8 +265,11 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     float m = (a.softmax_n > 0.f) ? 0.f : -INFINITY;   // running reference max (log2 domain)
     float l = a.softmax_n;                             // running sum, starts at n (the virtual zero-logit key)
 
+    TLF_DECL(1 + t)
+    TLF_ONLY(r == 0);
     for (int j = 0; j < n_t; ++j) {
       const int j0 = j * 128;
+      TLF(10);
       uint32_t kw[4];
       if constexpr (DROPOUT) {   // independent of S: issue before waiting for the tensor core
 #pragma unroll
@@ -243,7 +284,9 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld_x32(tS + 32, sr + 32);
         tmem_ld_x32(tS + 64, sr + 64);
         tmem_ld_x32(tS + 96, sr + 96);
+        TLF(11);
         tmem_wait_ld();
+        TLF(12);
       }
       if (generic) {
 #pragma unroll
@@ -259,7 +302,8 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
       }
-      if (j0 + 128 > warp_row_lim) {
+      const bool masked_tile = (j0 + 128 > warp_row_lim);      // warp-uniform
+      if (masked_tile) {
         const int lim = row_lim - j0;
 #pragma unroll
         for (int c = 0; c < 128; ++c) s[c] = (c < lim) ? s[c] : -INFINITY;
@@ -293,15 +337,12 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tmem_st_x32(tO + cb * 32, o);
         }
       }
+      TLF(13);
       const float m_use = (m == -INFINITY) ? 0.f : m;
       const float2 negm2 = make_float2(-m_use, -m_use);
       uint32_t pr[64];
       float2 l01 = make_float2(0.f, 0.f), l23 = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < 128; c += 4) {
-        const float2 a01 = __ffma2_rn(make_float2(s[c], s[c + 1]), cmul2, negm2);
-        const float2 a23 = __ffma2_rn(make_float2(s[c + 2], s[c + 3]), cmul2, negm2);
-        float p0 = ex2(a01.x), p1 = ex2(a01.y), p2 = ex2(a23.x), p3 = ex2(a23.y);
+      auto finish4 = [&](int c, float p0, float p1, float p2, float p3) {
         l01 = __fadd2_rn(l01, make_float2(p0, p1));
         l23 = __fadd2_rn(l23, make_float2(p2, p3));
         if constexpr (DROPOUT) {
@@ -313,13 +354,35 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         pr[c >> 1] = pack2<BF16>(p0, p1);
         pr[(c >> 1) + 1] = pack2<BF16>(p2, p3);
+      };
+      constexpr int kPolyCount = (D == 64 || DROPOUT) ? 1 : 0;
+      if (kPolyCount > 0 && !generic && !masked_tile) {
+        // interior tile, all scores finite: a fixed share of the exponentials runs as a polynomial on the FMA pipes
+#pragma unroll
+        for (int c = 0; c < 128; c += 4) {
+          const float2 a01 = __ffma2_rn(make_float2(s[c], s[c + 1]), cmul2, negm2);
+          const float2 a23 = __ffma2_rn(make_float2(s[c + 2], s[c + 3]), cmul2, negm2);
+          float p0 = ex2(a01.x), p1 = ex2(a01.y), p2, p3;
+          if (((c >> 2) % kPolyPeriod) < kPolyCount) { const float2 e = exp2_poly_pair(a23); p2 = e.x; p3 = e.y; }
+          else { p2 = ex2(a23.x); p3 = ex2(a23.y); }
+          finish4(c, p0, p1, p2, p3);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 128; c += 4) {
+          const float2 a01 = __ffma2_rn(make_float2(s[c], s[c + 1]), cmul2, negm2);
+          const float2 a23 = __ffma2_rn(make_float2(s[c + 2], s[c + 3]), cmul2, negm2);
+          finish4(c, ex2(a01.x), ex2(a01.y), ex2(a23.x), ex2(a23.y));
+        }
       }
       l += (l01.x + l01.y) + (l23.x + l23.y);
+      TLF(14);
       tmem_st_x32(tS, pr);
       tmem_st_x32(tS + 32, pr + 32);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      TLF(15);
     }
 
     // ------------------------------------------------------------------ epilogue

@@ -43,6 +43,27 @@ FASN_DEVICE float lg2(float x) {
   return y;
 }
 
+// 2^x for a pair of finite x <= ~100 on the FMA/ALU pipes instead of the MUFU (16 ex2/clk/SM is the scarcest
+// resource of the softmax): round-to-nearest range reduction with the 1.5*2^23 magic constant, degree-3 minimax
+// polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, below the 16-bit precision P is rounded to),
+// exponent inserted with one integer multiply-add.  Inputs below -126 return ~1e-38 (never exactly 0): callers
+// use it only on tiles without masked (-inf) scores.
+FASN_DEVICE float2 exp2_poly_pair(float2 x) {
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 p = __ffma2_rn(f, make_float2(0.055171654f, 0.055171654f), make_float2(0.24261113f, 0.24261113f));
+  p = __ffma2_rn(p, f, make_float2(0.69326097f, 0.69326097f));
+  p = __ffma2_rn(p, f, make_float2(0.99992806f, 0.99992806f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(t.x) * 0x800000 + __float_as_int(p.x));
+  r.y = __int_as_float(__float_as_int(t.y) * 0x800000 + __float_as_int(p.y));
+  return r;
+}
+
 // 3-input max (one FMNMX3 on sm_100)
 FASN_DEVICE float fmax3(float a, float b, float c) {
   float y;
@@ -236,6 +257,18 @@ FASN_DEVICE uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Split form for issue loops: the high word is a constant per operand kind, the low word is
+// (start address >> 4) | (LBO >> 4) << 16, so stepping through a tile is one 32-bit add of (bytes >> 4).
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
+FASN_DEVICE uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFF) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+FASN_DEVICE uint64_t umma_desc_join(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};\n" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
 
