@@ -46,6 +46,8 @@ WORKLOADS = {
                desc="BASELINE.json configs[2]: fwd+bwd fp16 B=4 H=32 S=4096 D=128 n=0.5 causal dropout=0.1"),
     "c3bf16": dict(B=4, H=32, S=4096, D=128, dtype="bf16", n=0.5, causal=True, dropout=0.1, bwd=True,
                    desc="configs[2] in bf16"),
+    "c3nd": dict(B=4, H=32, S=4096, D=128, dtype="f16", n=0.5, causal=True, dropout=0.0, bwd=True,
+                 desc="configs[2] without dropout (diagnostic)"),
     "c2": dict(B=8, H=16, S=2048, D=64, dtype="bf16", n=1.0, causal=False, dropout=0.0, bwd=False,
                desc="BASELINE.json configs[1]: fwd bf16 B=8 H=16 S=2048 D=64 n=1 non-causal"),
     "c4": dict(B=8, H=40, S=8192, D=128, dtype="bf16", n=1.0, causal=True, dropout=0.0, bwd=False,
@@ -274,25 +276,21 @@ def run_ours(args, w):
     value = world * flops_step * args.steps / (ms_max * 1e-3) / 1e12
 
     # ---- end to end: host buffers through the public API ----------------------------------------------------
+    # flash_attention_softmax_n.host.attention_host: pinned host tensors in, pinned host tensors out; chunks of
+    # (batch, head) units are pipelined over three streams so H2D, kernels and D2H overlap.
     e2e = None
     if not args.no_e2e:
-        hq, hk, hv, hdo = (torch.empty(B, H, S, D, dtype=dtype).normal_(0, 0.5).pin_memory() for _ in range(4))
-        outs = [torch.empty(B, H, S, D, dtype=dtype).pin_memory() for _ in range(4 if w["bwd"] else 1)]
+        from flash_attention_softmax_n.host import HostPipeline
+        hq, hk, hv, hdo = (torch.empty(units, S, D, dtype=dtype).normal_(0, 0.5).pin_memory() for _ in range(4))
+        ho = torch.empty(units, S, D, dtype=dtype).pin_memory()
+        hg = tuple(torch.empty(units, S, D, dtype=dtype).pin_memory() for _ in range(3)) if w["bwd"] else None
+        pipe = HostPipeline(units, S, S, D, dtype, dev, chunks=args.e2e_chunks, backward=w["bwd"])
+        ekw = dict(softmax_n_param=w["n"], is_causal=w["causal"], dropout_p=w["dropout"])
 
         def e2e_step(i):
-            dq_, dk_, dv_ = (t_.to(dev, non_blocking=True) for t_ in (hq, hk, hv))
-            if w["bwd"]:
-                dq_.requires_grad_(); dk_.requires_grad_(); dv_.requires_grad_()
-                ddo = hdo.to(dev, non_blocking=True)
             if w["dropout"] > 0:
-                kw["_philox"] = (0x5EED, 1000 + i)
-            o = flash_attention_n(dq_, dk_, dv_, **kw)
-            outs[0].copy_(o.detach(), non_blocking=True)
-            if w["bwd"]:
-                o.backward(ddo)
-                outs[1].copy_(dq_.grad, non_blocking=True)
-                outs[2].copy_(dk_.grad, non_blocking=True)
-                outs[3].copy_(dv_.grad, non_blocking=True)
+                ekw["_philox"] = (0x5EED, 1000 + i)
+            pipe.run(hq, hk, hv, hdo if w["bwd"] else None, ho, hg, **ekw)      # returns with the results on the host
 
         for i in range(2):
             e2e_step(i)
@@ -307,10 +305,11 @@ def run_ours(args, w):
         t2 = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if distributed:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        nbytes = B * H * S * D * 2
+        nbytes = units * S * D * 2
         e2e = {"value": world * flops_step * n_e2e / (t2.item() * 1e-3) / 1e12, "unit": "TFLOP/s",
-               "h2d_bytes_per_step": nbytes * (4 if w["bwd"] else 3), "d2h_bytes_per_step": nbytes * len(outs),
-               "ms_per_step": t2.item() / n_e2e, "steps": n_e2e}
+               "h2d_bytes_per_step": nbytes * (4 if w["bwd"] else 3), "d2h_bytes_per_step": nbytes * (4 if w["bwd"] else 1),
+               "ms_per_step": t2.item() / n_e2e, "steps": n_e2e,
+               "api": f"flash_attention_softmax_n.host.attention_host, {pipe.chunks} chunks of units pipelined over 3 streams"}
 
     # ---- roofline of the dominant kernel --------------------------------------------------------------------
     peaks = measured_peaks()
@@ -361,6 +360,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--flush-l2", action="store_true", help="write 256 MiB between steps (default for small workloads)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget inside the default run")
     ap.add_argument("--cpu-step-seconds", type=float, default=6.0, help="--impl reference: CPU seconds per step")

@@ -53,7 +53,7 @@ template <int D> struct FwdCfg {
   static constexpr int DB = D / 64;                      // 128-byte blocks per row
   static constexpr int TILE_BYTES = 128 * D * 2;
   static constexpr int BLK_BYTES = 128 * 128;
-  static constexpr int NUM_BARS = 8 + 4 * NS;
+  static constexpr int NUM_BARS = 10 + 4 * NS;
   static constexpr int SMEM_BYTES = 1024 + (2 + 2 * NS) * TILE_BYTES + NUM_BARS * 8 + 16;
 };
 
@@ -63,6 +63,9 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const FwdArgs a) {
   using Cfg = FwdCfg<D>;
   constexpr int NS = Cfg::NS, DB = Cfg::DB, TILE_BYTES = Cfg::TILE_BYTES, BLK_BYTES = Cfg::BLK_BYTES;
+  // D=128: P is handed to the tensor pipe in two halves (measured +6 % at S=8192); at D=64 the MMAs are too short
+  // for the extra barrier round to pay (-3 %), so P is handed over whole.
+  constexpr bool kSplitPV = (D == 128);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,13 +116,14 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* k_empty = k_full + NS;       // [NS]
   uint64_t* v_full = k_empty + NS;       // [NS]
   uint64_t* v_empty = v_full + NS;       // [NS]
+  uint64_t* p_full2 = v_empty + NS;      // [2]  second half (keys 64..127) of P_t written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NUM_BARS);
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_o);
   }
   if (warp == 9 && lane == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&o_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 128); mbar_init(&p_full2[i], 128); mbar_init(&o_full[i], 1); }
     for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     fence_mbar_init();
     fence_proxy_async_smem();
@@ -177,11 +181,15 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           umma_ss(tm + t * 128, umma_desc_join(a0 + off, hi_desc), umma_desc_join(b0 + off, hi_desc), idesc_qk, kb > 0 ? 1u : 0u);
         }
       };
-      auto issue_pv = [&](int t, int s, uint32_t acc) {
+      // P.V is issued in two halves (keys 0..63, then 64..127 of the tile) so the first half runs on the tensor pipe
+      // while the softmax warps are still producing the second half of P
+      auto issue_pv_half = [&](int t, int s, int half, uint32_t acc) {
         const uint32_t b0 = v_lo + s * (TILE_BYTES >> 4);
 #pragma unroll
-        for (int kb = 0; kb < 8; ++kb)
-          umma_ts(tm + 256 + t * D, tm + t * 128 + kb * 8, umma_desc_join(b0 + kb * (2048 >> 4), hi_desc), idesc_pv, kb > 0 ? 1u : acc);
+        for (int kb = 0; kb < 4; ++kb) {
+          const int k = half * 4 + kb;
+          umma_ts(tm + 256 + t * D, tm + t * 128 + k * 8, umma_desc_join(b0 + k * (2048 >> 4), hi_desc), idesc_pv, (half > 0 || kb > 0) ? 1u : acc);
+        }
       };
       TLF_DECL(0)
       TLF_ONLY(lane == 0);
@@ -208,8 +216,15 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(&p_full[0], j & 1);
           tc_fence_after();
           TLF(2);
+          if (kSplitPV) {
+            if (elect_one()) issue_pv_half(0, s, 0, j > 0 ? 1u : 0u);
+            __syncwarp();
+            mbar_wait(&p_full2[0], j & 1);
+            tc_fence_after();
+          }
           if (elect_one()) {
-            issue_pv(0, s, j > 0 ? 1u : 0u);
+            if (!kSplitPV) issue_pv_half(0, s, 0, j > 0 ? 1u : 0u);
+            issue_pv_half(0, s, 1, 1u);
             tc_commit(&o_full[0]);
             if (j + 1 < n_tiles0) { issue_qk(0, s1); tc_commit(&s_full[0]); }
           }
@@ -219,8 +234,15 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(&p_full[1], j & 1);
           tc_fence_after();
           TLF(3);
+          if (kSplitPV) {
+            if (elect_one()) issue_pv_half(1, s, 0, j > 0 ? 1u : 0u);
+            __syncwarp();
+            mbar_wait(&p_full2[1], j & 1);
+            tc_fence_after();
+          }
           if (elect_one()) {
-            issue_pv(1, s, j > 0 ? 1u : 0u);
+            if (!kSplitPV) issue_pv_half(1, s, 0, j > 0 ? 1u : 0u);
+            issue_pv_half(1, s, 1, 1u);
             tc_commit(&o_full[1]);
             if (j + 1 < n_tiles1) { issue_qk(1, s1); tc_commit(&s_full[1]); }
           }
@@ -356,32 +378,38 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         pr[(c >> 1) + 1] = pack2<BF16>(p2, p3);
       };
       constexpr int kPolyCount = (D == 64 || DROPOUT) ? 1 : 0;
-      if (kPolyCount > 0 && !generic && !masked_tile) {
-        // interior tile, all scores finite: a fixed share of the exponentials runs as a polynomial on the FMA pipes
+      const bool use_poly = kPolyCount > 0 && !generic && !masked_tile;
 #pragma unroll
-        for (int c = 0; c < 128; c += 4) {
-          const float2 a01 = __ffma2_rn(make_float2(s[c], s[c + 1]), cmul2, negm2);
-          const float2 a23 = __ffma2_rn(make_float2(s[c + 2], s[c + 3]), cmul2, negm2);
-          float p0 = ex2(a01.x), p1 = ex2(a01.y), p2, p3;
-          if (((c >> 2) % kPolyPeriod) < kPolyCount) { const float2 e = exp2_poly_pair(a23); p2 = e.x; p3 = e.y; }
-          else { p2 = ex2(a23.x); p3 = ex2(a23.y); }
-          finish4(c, p0, p1, p2, p3);
-        }
-      } else {
+      for (int hf = 0; hf < 2; ++hf) {
+        if (use_poly) {
+          // interior tile, all scores finite: a fixed share of the exponentials runs as a polynomial on the FMA pipes
 #pragma unroll
-        for (int c = 0; c < 128; c += 4) {
-          const float2 a01 = __ffma2_rn(make_float2(s[c], s[c + 1]), cmul2, negm2);
-          const float2 a23 = __ffma2_rn(make_float2(s[c + 2], s[c + 3]), cmul2, negm2);
-          finish4(c, ex2(a01.x), ex2(a01.y), ex2(a23.x), ex2(a23.y));
+          for (int c = hf * 64; c < hf * 64 + 64; c += 4) {
+            const float2 a01 = __ffma2_rn(make_float2(s[c], s[c + 1]), cmul2, negm2);
+            const float2 a23 = __ffma2_rn(make_float2(s[c + 2], s[c + 3]), cmul2, negm2);
+            float p0 = ex2(a01.x), p1 = ex2(a01.y), p2, p3;
+            if (((c >> 2) % kPolyPeriod) < kPolyCount) { const float2 e = exp2_poly_pair(a23); p2 = e.x; p3 = e.y; }
+            else { p2 = ex2(a23.x); p3 = ex2(a23.y); }
+            finish4(c, p0, p1, p2, p3);
+          }
+        } else {
+#pragma unroll
+          for (int c = hf * 64; c < hf * 64 + 64; c += 4) {
+            const float2 a01 = __ffma2_rn(make_float2(s[c], s[c + 1]), cmul2, negm2);
+            const float2 a23 = __ffma2_rn(make_float2(s[c + 2], s[c + 3]), cmul2, negm2);
+            finish4(c, ex2(a01.x), ex2(a01.y), ex2(a23.x), ex2(a23.y));
+          }
         }
+        // P columns [32 hf, 32 hf + 32) <- keys [64 hf, 64 hf + 64): over S columns this thread has already read
+        tmem_st_x32(tS + hf * 32, pr + hf * 32);
+        if (kSplitPV || hf == 1) {
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive((kSplitPV && hf == 1) ? &p_full2[t] : &p_full[t]);
+        }
+        if (hf == 0) TLF(14);
       }
       l += (l01.x + l01.y) + (l23.x + l23.y);
-      TLF(14);
-      tmem_st_x32(tS, pr);
-      tmem_st_x32(tS + 32, pr + 32);
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&p_full[t]);
       TLF(15);
     }
 

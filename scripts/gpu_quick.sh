@@ -11,11 +11,11 @@ except Exception as e:
     print("bench parse failed", e)
 PY
 tail -n 5 gpurun_out/bench_c3_$TAG.err
-for wl in c2 c4 c5; do
+for wl in c3nd c2 c4 c5; do
   timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_${wl}_$TAG.json 2> gpurun_out/bench_${wl}_$TAG.err; python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/bench_${wl}_$TAG.json")); print("$wl: %.1f TFLOP/s  %.3f ms" % (d["value"], d["ms_per_step"]))
+    d=json.load(open("gpurun_out/bench_${wl}_$TAG.json")); r=d["roofline"]; print("$wl: %.1f TFLOP/s  %.3f ms  (fwd kernel %.3f ms, main kernel %.3f ms)" % (d["value"], d["ms_per_step"], r["fwd_kernel_ms"], r["kernel_ms"]))
 except Exception as e:
     print("$wl failed", e)
 PY

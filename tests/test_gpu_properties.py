@@ -95,3 +95,24 @@ def test_host_buffer_entry_point(fasn_lib):
     assert torch.equal(outs[0], o.detach().cpu())
     assert torch.equal(outs[2], k.grad.cpu()) and torch.equal(outs[3], v.grad.cpu())
     assert orc.rel_l2(outs[1], q.grad) < 1e-3         # dQ is reduced with fp32 adds whose order is not fixed
+
+
+def test_attention_host_pipeline_matches_device_call(fasn_lib):
+    """Host tensors in / out, chunks of units pipelined over streams: same bits as one device call (dQ: fp32 add order)."""
+    from flash_attention_softmax_n import flash_attention_n
+    from flash_attention_softmax_n.host import attention_host
+    g = torch.Generator().manual_seed(2)
+    b, h, l, s, d = 2, 5, 256, 384, 128
+    hq = (torch.randn(b, h, l, d, generator=g) * 0.5).to(torch.bfloat16)
+    hk, hv = ((torch.randn(b, h, s, d, generator=g) * 0.5).to(torch.bfloat16) for _ in range(2))
+    hdo = torch.randn(b, h, l, d, generator=g).to(torch.bfloat16)
+    kw = dict(softmax_n_param=0.5, is_causal=True, dropout_p=0.1, _philox=(21, 6))
+    o, dq, dk, dv = attention_host(hq, hk, hv, hdo, chunks=4, **kw)
+    assert not o.is_cuda and o.shape == (b, h, l, d)
+    q, k, v = (t.cuda().requires_grad_() for t in (hq, hk, hv))
+    ref = flash_attention_n(q, k, v, **kw)
+    ref.backward(hdo.cuda())
+    assert torch.equal(o, ref.detach().cpu()) and torch.equal(dk, k.grad.cpu()) and torch.equal(dv, v.grad.cpu())
+    assert orc.rel_l2(dq, q.grad) < 2e-3
+    o2 = attention_host(hq, hk, hv, chunks=3, **kw)          # forward only
+    assert torch.equal(o2, o)
