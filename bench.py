@@ -48,6 +48,10 @@ WORKLOADS = {
                    desc="configs[2] in bf16"),
     "c3nd": dict(B=4, H=32, S=4096, D=128, dtype="f16", n=0.5, causal=True, dropout=0.0, bwd=True,
                  desc="configs[2] without dropout (diagnostic)"),
+    "c3pad": dict(B=4, H=32, S=4096, D=128, dtype="f16", n=0.5, causal=True, dropout=0.0, bwd=True, aux="padmask",
+                  desc="configs[2] shape, no dropout, dense key-padding attn_mask (B,1,1,S) AND causal (diagnostic)"),
+    "c3alibi": dict(B=2, H=16, S=4096, D=128, dtype="f16", n=0.5, causal=True, dropout=0.0, bwd=True, aux="alibi",
+                    desc="B=2 H=16 S=4096 D=128 with a dense ALiBi attn_bias (H,L,S) (diagnostic; 512 MiB of bias per pass)"),
     "c2": dict(B=8, H=16, S=2048, D=64, dtype="bf16", n=1.0, causal=False, dropout=0.0, bwd=False,
                desc="BASELINE.json configs[1]: fwd bf16 B=8 H=16 S=2048 D=64 n=1 non-causal"),
     "c4": dict(B=8, H=40, S=8192, D=128, dtype="bf16", n=1.0, causal=True, dropout=0.0, bwd=False,
@@ -222,6 +226,13 @@ def run_ours(args, w):
     v = torch.empty(B, H, S, D, device=dev, dtype=dtype).normal_(0, 0.5).requires_grad_(w["bwd"])
     do = torch.randn(B, H, S, D, device=dev, dtype=dtype)
     kw = dict(softmax_n_param=w["n"], is_causal=w["causal"], dropout_p=w["dropout"], _bh_offset=rank * units)
+    if w.get("aux") == "padmask":
+        lens = torch.randint(S // 2, S + 1, (B,), device=dev)
+        kw["attn_mask"] = (torch.arange(S, device=dev)[None, :] < lens[:, None]).view(B, 1, 1, S)
+    elif w.get("aux") == "alibi":
+        slopes = 2.0 ** (-8.0 * torch.arange(1, H + 1, device=dev) / H)
+        dist_ = (torch.arange(S, device=dev)[None, :] - torch.arange(S, device=dev)[:, None]).float()
+        kw["attn_bias"] = (slopes[:, None, None] * dist_[None]).to(dtype)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if args.flush_l2 else None
 
     def step(i):
@@ -279,7 +290,7 @@ def run_ours(args, w):
     # flash_attention_softmax_n.host.attention_host: pinned host tensors in, pinned host tensors out; chunks of
     # (batch, head) units are pipelined over three streams so H2D, kernels and D2H overlap.
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not w.get("aux"):
         from flash_attention_softmax_n.host import HostPipeline
         hq, hk, hv, hdo = (torch.empty(units, S, D, dtype=dtype).normal_(0, 0.5).pin_memory() for _ in range(4))
         ho = torch.empty(units, S, D, dtype=dtype).pin_memory()
@@ -360,7 +371,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--flush-l2", action="store_true", help="write 256 MiB between steps (default for small workloads)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-chunks", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget inside the default run")
     ap.add_argument("--cpu-step-seconds", type=float, default=6.0, help="--impl reference: CPU seconds per step")

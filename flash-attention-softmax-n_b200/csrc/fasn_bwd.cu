@@ -377,14 +377,30 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       const float* lse_s = sLse + s * 128 + half * 64;
       if (has_aux) {
-        // generic path: bias added / mask applied in the log2 domain before the exponent
+        // generic path: bias added / mask applied in the log2 domain before the exponent.  This thread walks down a
+        // column of the dense (L, S) bias / mask (fixed key, 64 queries): the 32 lanes of a warp read 32 consecutive
+        // keys, so every load instruction is one coalesced segment; pointers advance by the row stride.
+        const bool full_q = (qi0 + 128 <= a.Sq);            // no query row of this tile lies beyond Sq
+        const uint16_t* bp = bbase ? bbase + (long long)min(qc0, a.Sq - 1) * a.bias.sq : nullptr;
+        const uint8_t* mp = mbase ? mbase + (long long)min(qc0, a.Sq - 1) * a.mask.sq : nullptr;
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          float x = p[c] * a.scale_log2;
-          const long long q_c = min(qc0 + c, a.Sq - 1);
-          if (bbase) x = fmaf(cvt16_to_f32<BF16>(bbase[q_c * a.bias.sq]), kLog2e, x);
-          if (mbase && mbase[q_c * a.mask.sq] == 0) x = -INFINITY;
-          p[c] = ex2(x - lse_s[c]);
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          float bv[16];
+          uint32_t mbits = 0xFFFFu;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const bool in_q = full_q || (qc0 + c0 + e < a.Sq);
+            bv[e] = 0.f;
+            if (bp) { if (in_q) bv[e] = cvt16_to_f32<BF16>(*bp); bp += a.bias.sq; }
+            if (mp) { if (in_q && *mp == 0) mbits &= ~(1u << e); mp += a.mask.sq; }
+          }
+          const float4* l4p = reinterpret_cast<const float4*>(lse_s + c0);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float lse_e = reinterpret_cast<const float*>(l4p)[e];
+            float x = fmaf(p[c0 + e], a.scale_log2, bv[e] * kLog2e);
+            p[c0 + e] = ((mbits >> e) & 1u) ? ex2(x - lse_e) : 0.f;
+          }
         }
       } else {
 #pragma unroll

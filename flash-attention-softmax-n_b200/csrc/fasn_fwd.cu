@@ -314,12 +314,44 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 128; ++c) s[c] *= a.scale_log2;
         if (has_aux) {
+          // dense bias / mask rows of this thread: 16-byte loads where the row segment is aligned and in range
+          // (each thread streams its own 256 B / 128 B per tile; lines are shared by consecutive instructions via L1)
+          if (brow) {
 #pragma unroll
-          for (int c = 0; c < 128; ++c) {
-            const int col = j0 + c;
-            if (col < a.Skv) {
-              if (brow) s[c] = fmaf(cvt16_to_f32<BF16>(brow[col]), kLog2e, s[c]);
-              if (mrow && mrow[col] == 0) s[c] = -INFINITY;
+            for (int g = 0; g < 16; ++g) {                    // 8 bias elements per 16-byte load
+              const int col = j0 + g * 8;
+              const uint16_t* p = brow + col;
+              if (col + 8 <= a.Skv && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+                const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(p));
+                const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  s[g * 8 + 2 * e] = fmaf(cvt16_to_f32<BF16>(w[e] & 0xFFFF), kLog2e, s[g * 8 + 2 * e]);
+                  s[g * 8 + 2 * e + 1] = fmaf(cvt16_to_f32<BF16>(w[e] >> 16), kLog2e, s[g * 8 + 2 * e + 1]);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (col + e < a.Skv) s[g * 8 + e] = fmaf(cvt16_to_f32<BF16>(p[e]), kLog2e, s[g * 8 + e]);
+              }
+            }
+          }
+          if (mrow) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {                     // 16 mask bytes per 16-byte load
+              const int col = j0 + g * 16;
+              const uint8_t* p = mrow + col;
+              if (col + 16 <= a.Skv && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+                const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(p));
+                const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  if (((w[e >> 2] >> (8 * (e & 3))) & 0xFF) == 0) s[g * 16 + e] = -INFINITY;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  if (col + e < a.Skv && p[e] == 0) s[g * 16 + e] = -INFINITY;
+              }
             }
           }
         }

@@ -11,7 +11,7 @@ except Exception as e:
     print("bench parse failed", e)
 PY
 tail -n 5 gpurun_out/bench_c3_$TAG.err
-for wl in c3nd c2 c4 c5; do
+for wl in c3nd c3pad c3alibi c2 c4 c5; do
   timeout 300 python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_${wl}_$TAG.json 2> gpurun_out/bench_${wl}_$TAG.err; python - <<PY
 import json
 try:

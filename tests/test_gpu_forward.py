@@ -138,3 +138,32 @@ def test_forward_strided_inputs_and_errors(fasn_lib):
         flash_attention_n(q.float(), k.float(), v.float())
     with pytest.raises(NotImplementedError):
         flash_attention_n(q[..., :32], k[..., :32], v[..., :32])
+
+
+@pytest.mark.parametrize("scale", [-0.2, 0.0])
+def test_forward_backward_non_positive_scale(fasn_lib, scale):
+    """A non-positive logit scale takes the generic (pre-scaling) path: the running max must follow the scaled scores."""
+    from tests._util import run_fused, oracle_all
+    dtype = torch.float16
+    q, k, v, do = make_qkv(1, 2, 200, 264, 64, dtype, seed=41)
+    kw = dict(softmax_n_param=1.0, scale=scale, is_causal=True)
+    got = run_fused(q, k, v, do, **kw)
+    want = oracle_all(q, k, v, do, **kw)
+    for name, a, b in zip(("O", "dQ", "dK", "dV"), got, want):
+        check_close(f"{name}(scale={scale})", a, b, None, dtype, rel_scale=1.5)
+
+
+def test_forward_long_sequence_rows(fasn_lib):
+    """BASELINE.json configs[4] shape for one head (S = 65536, D = 64, bf16, n = 1, causal): the first and the last 128
+    query rows against the float64 oracle evaluated on just those rows (bottom-right alignment makes a row block of the
+    full problem equal to a smaller causal problem with S_kv = last visible key + 1)."""
+    from flash_attention_softmax_n import flash_attention_n
+    dtype, S, D = torch.bfloat16, 65536, 64
+    g = torch.Generator().manual_seed(65)
+    q, k, v = ((torch.randn(1, 1, S, D, generator=g) * 0.5).to(dtype).cuda() for _ in range(3))
+    out = flash_attention_n(q, k, v, softmax_n_param=1.0, is_causal=True)
+    torch.cuda.synchronize()
+    for lo, hi in ((0, 128), (S - 128, S), (30000, 30100)):
+        want = orc.slow_attention_n(q[:, :, lo:hi].double().cpu(), k[:, :, :hi].double().cpu(), v[:, :, :hi].double().cpu(),
+                                    softmax_n_param=1.0, is_causal=True)
+        check_close(f"O[{lo}:{hi}]", out[:, :, lo:hi], want, None, dtype)
