@@ -154,9 +154,6 @@ uint32_t keep_threshold(float dropout_p) {
   return (uint32_t)t;
 }
 
-fasn::PhiloxKey philox_key(uint64_t seed, uint64_t offset) {
-  return fasn::PhiloxKey{(uint32_t)(seed & 0xFFFFFFFFull), (uint32_t)(seed >> 32), (uint32_t)(offset & 0xFFFFFFFFull)};
-}
 
 }  // namespace
 
@@ -202,7 +199,7 @@ int fasn_fwd(const FasnParams* p) {
   a.bias = aux_view(p->bias);
   a.drop_thr = keep_threshold(p->dropout_p);
   a.inv_keep = 1.0f / (1.0f - p->dropout_p);
-  a.key = philox_key(p->philox_seed, p->philox_offset);
+  a.key = fasn::make_philox_key(p->philox_seed, p->philox_offset, a.drop_thr);
   a.bh_offset = (uint32_t)p->bh_offset;
 #ifdef FASN_TIMELINE
   {
@@ -259,7 +256,7 @@ int fasn_bwd(const FasnParams* p) {
   a.bias = aux_view(p->bias);
   a.drop_thr = keep_threshold(p->dropout_p);
   a.inv_keep = 1.0f / (1.0f - p->dropout_p);
-  a.key = philox_key(p->philox_seed, p->philox_offset);
+  a.key = fasn::make_philox_key(p->philox_seed, p->philox_offset, a.drop_thr);
   a.bh_offset = (uint32_t)p->bh_offset;
 #ifdef FASN_TIMELINE
   {
@@ -313,7 +310,7 @@ int fasn_dropout_mask(uint8_t* out, int32_t batch, int32_t heads, int32_t seqlen
   if (out == nullptr || batch <= 0 || heads <= 0 || seqlen_q <= 0 || seqlen_kv <= 0) return fail(FASN_EINVAL, "bad argument");
   if (!(dropout_p >= 0.f && dropout_p < 1.f)) return fail(FASN_EINVAL, "dropout_p must be in [0,1)");
   cudaError_t e = fasn::launch_dropout_mask(out, batch, heads, seqlen_q, seqlen_kv, keep_threshold(dropout_p),
-                                            philox_key(philox_seed, philox_offset), (uint32_t)bh_offset, (cudaStream_t)stream);
+                                            fasn::make_philox_key(philox_seed, philox_offset, keep_threshold(dropout_p)), (uint32_t)bh_offset, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda(e, "fasn_dropout_mask launch");
   return 0;
 }

@@ -422,13 +422,11 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         uint32_t pk[32];
 #pragma unroll
         for (int c = 0; c < 64; c += 2) {
-          float x0 = p[c], x1 = p[c + 1];
-          if constexpr (DROPOUT) {      // the 1/(1-p) factor of the kept entries is applied to dV in the epilogue
-            const uint32_t w = (c < 32) ? keep0 : keep1;
-            x0 = (w & (1u << (c & 31))) ? x0 : 0.f;
-            x1 = (w & (1u << ((c + 1) & 31))) ? x1 : 0.f;
-          }
-          pk[c >> 1] = pack2<BF16>(x0, x1);
+          uint32_t w01 = pack2<BF16>(p[c], p[c + 1]);
+          // dropped entries are zeroed on the packed pair (1 PRMT + 1 AND per two elements); the 1/(1-p) factor of the
+          // kept entries is applied to dV in the epilogue
+          if constexpr (DROPOUT) w01 &= keep_pair_mask((c < 32) ? keep0 : keep1, c & 31);
+          pk[c >> 1] = w01;
         }
         tmem_st_x32(tmem_base + lane_off + TM_S + half * 64, pk);   // over this thread's own S^T columns only
         tmem_wait_st();

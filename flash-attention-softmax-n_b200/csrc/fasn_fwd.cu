@@ -399,15 +399,14 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       auto finish4 = [&](int c, float p0, float p1, float p2, float p3) {
         l01 = __fadd2_rn(l01, make_float2(p0, p1));
         l23 = __fadd2_rn(l23, make_float2(p2, p3));
-        if constexpr (DROPOUT) {
+        uint32_t w01 = pack2<BF16>(p0, p1), w23 = pack2<BF16>(p2, p3);
+        if constexpr (DROPOUT) {     // zero the dropped entries on the packed pairs: 1 PRMT + 1 AND per two elements
           const uint32_t w = kw[c >> 5];
-          p0 = (w & (1u << ((c + 0) & 31))) ? p0 : 0.f;
-          p1 = (w & (1u << ((c + 1) & 31))) ? p1 : 0.f;
-          p2 = (w & (1u << ((c + 2) & 31))) ? p2 : 0.f;
-          p3 = (w & (1u << ((c + 3) & 31))) ? p3 : 0.f;
+          w01 &= keep_pair_mask(w, c & 31);
+          w23 &= keep_pair_mask(w, (c + 2) & 31);
         }
-        pr[c >> 1] = pack2<BF16>(p0, p1);
-        pr[(c >> 1) + 1] = pack2<BF16>(p2, p3);
+        pr[c >> 1] = w01;
+        pr[(c >> 1) + 1] = w23;
       };
       constexpr int kPolyCount = (D == 64 || DROPOUT) ? 1 : 0;
       const bool use_poly = kPolyCount > 0 && !generic && !masked_tile;

@@ -84,6 +84,20 @@ FASN_DEVICE uint32_t warp_transpose_bits(uint32_t x, int lane) {
   return x;
 }
 
+// Mask for a packed pair of 16-bit values from two adjacent keep bits: 0xFFFF in the low half iff bit `pos` of w is
+// set, 0xFFFF in the high half iff bit `pos + 1` is set (pos even, compile-time after unrolling).  w << t puts bit
+// 8 b + 7 - t in the sign position of byte b; PRMT with the sign-replicate flag (selector | 8) expands those sign
+// bits to whole bytes, so the mask costs one PRMT (the shifted copies of w are shared by the whole 32-key group).
+FASN_DEVICE uint32_t keep_pair_mask(uint32_t w, int pos) {
+  const int b = pos >> 3;                        // both bits live in byte b
+  const uint32_t x_lo = w << (7 - (pos & 7));    // bit pos     -> sign of byte b
+  const uint32_t x_hi = w << (6 - (pos & 7));    // bit pos + 1 -> sign of byte b
+  const uint32_t sel = (uint32_t)(b | 8) | ((uint32_t)(b | 8) << 4) | ((uint32_t)((4 + b) | 8) << 8) | ((uint32_t)((4 + b) | 8) << 12);
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %2, %3;\n" : "=r"(m) : "r"(x_lo), "r"(x_hi), "r"(sel));
+  return m;
+}
+
 // pack two fp32 into one 32-bit word of two 16-bit floats; `lo` lands in bits [0,16)
 template <bool BF16> FASN_DEVICE uint32_t pack2(float lo, float hi) {
   uint32_t r;
