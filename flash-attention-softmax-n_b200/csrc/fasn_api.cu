@@ -46,7 +46,7 @@ EncodeTiledFn encode_tiled() {
 
 // (D, S, H, B) 16-bit tensor, box = 64 x 128 x 1 x 1, 128-byte swizzle, out-of-bounds rows read as zero.
 int make_map(CUtensorMap* m, const void* ptr, long long sb, long long sh, long long ss, int B, int H, int S, int D,
-             bool bf16, const char* name) {
+             bool bf16, const char* name, int box_rows = 128) {
   EncodeTiledFn fn = encode_tiled();
   if (!fn) return fail(FASN_EDRIVER, "cuTensorMapEncodeTiled is not available from this driver");
   if (ptr == nullptr) return fail(FASN_EINVAL, "%s: null pointer", name);
@@ -58,7 +58,7 @@ int make_map(CUtensorMap* m, const void* ptr, long long sb, long long sh, long l
   if ((sh % 8) != 0 || (sb % 8) != 0) return fail(FASN_EUNSUPPORTED, "%s: head/batch strides must be multiples of 8 elements", name);
   cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)ss * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
-  cuuint32_t box[4] = {64, 128, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims,
                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -316,12 +316,22 @@ int fasn_dropout_mask(uint8_t* out, int32_t batch, int32_t heads, int32_t seqlen
 }
 
 int fasn_probe(int mode, uint32_t dtype, const void* x, const void* y, float* c, void* stream) {
-  if (mode < 0 || mode > 3 || x == nullptr || y == nullptr || c == nullptr) return fail(FASN_EINVAL, "bad argument");
+  if (!((mode >= 0 && mode <= 3) || (mode >= 10 && mode <= 12)) || x == nullptr || y == nullptr || c == nullptr) return fail(FASN_EINVAL, "bad argument");
   if (dtype != FASN_FP16 && dtype != FASN_BF16) return fail(FASN_EUNSUPPORTED, "dtype");
   const bool bf16 = dtype == FASN_BF16;
   DeviceGuard guard(x);
   if (guard.err != cudaSuccess) return fail_cuda(guard.err, "x is not a device pointer / cannot bind its device");
   CUtensorMap tx, ty;
+  if (mode >= 10) {     // CTA-pair forms: x is 256x128, y is 128x128 (modes 10, 12) or 256x128 (mode 11)
+    const int yrows = mode == 11 ? 256 : 128;
+    CUtensorMap ty64;
+    if (int rc = make_map(&tx, x, 0, 0, 128, 1, 1, 256, 128, bf16, "x")) return rc;
+    if (int rc = make_map(&ty, y, 0, 0, 128, 1, 1, yrows, 128, bf16, "y")) return rc;
+    if (int rc = make_map(&ty64, y, 0, 0, 128, 1, 1, yrows, 128, bf16, "y", 64)) return rc;
+    cudaError_t e = fasn::launch_probe_pair(mode, bf16, tx, ty, ty64, x, c, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail_cuda(e, "fasn_probe (pair) launch");
+    return 0;
+  }
   if (int rc = make_map(&tx, x, 0, 0, 128, 1, 1, 128, 128, bf16, "x")) return rc;
   if (int rc = make_map(&ty, y, 0, 0, 128, 1, 1, 128, 128, bf16, "y")) return rc;
   cudaError_t e = fasn::launch_probe(mode, bf16, tx, ty, x, c, (cudaStream_t)stream);

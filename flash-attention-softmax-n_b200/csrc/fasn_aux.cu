@@ -107,7 +107,145 @@ fasn_probe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
+// CTA-pair probe (cluster of 2, tcgen05 cta_group::2): the operand forms of the paired backward kernel (fasn_bwd2.cu).
+//   mode 10: C[256x128] = X[256x128] Y[128x128]^T   M=256 SS, both K-major; B split along N (64 rows of Y per CTA)
+//   mode 11: C[128x128] = X[256x128]^T Y[256x128]   M=128 SS, A and B MN-major, K = 256; A is written with generic
+//            (local and remote st.shared::cluster) stores by both CTAs, as the dS exchange of the backward does
+//   mode 12: C[256x128] = X[256x128] Y[128x128]     M=256 TS, A in each CTA's TMEM, B MN-major split along N
+template <bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(160, 1)
+fasn_probe_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
+                       const __grid_constant__ CUtensorMap tm_y64, int mode, const uint16_t* __restrict__ x,
+                       float* __restrict__ c) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                 // 32 KB
+  uint8_t* sB = smem + 32768;         // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 32768);   // [0] tma (leader), [1] mma done (both), [2] A ready (leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cr = cluster_ctarank();
+
+  if (warp == 4 && lane == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 8);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 0) { tmem_alloc_pair<512>(tmem_slot); tmem_relinquish_pair(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      if (mode == 10) {
+        if (cr == 0) mbar_arrive_expect_tx(&bars[0], 2 * (32768 + 16384));
+        for (int db = 0; db < 2; ++db) {
+          tma_load_4d_pair(sA + db * 16384, &tm_x, &bars[0], db * 64, 128 * cr, 0, 0);
+          tma_load_4d_pair(sB + db * 8192, &tm_y64, &bars[0], db * 64, 64 * cr, 0, 0);
+        }
+      } else if (mode == 11) {
+        if (cr == 0) mbar_arrive_expect_tx(&bars[0], 2 * 32768);
+        tma_load_4d_pair(sB, &tm_y, &bars[0], 64 * cr, 0, 0, 0);
+        tma_load_4d_pair(sB + 16384, &tm_y, &bars[0], 64 * cr, 128, 0, 0);
+      } else {
+        if (cr == 0) mbar_arrive_expect_tx(&bars[0], 2 * 16384);
+        tma_load_4d_pair(sB, &tm_y, &bars[0], 64 * cr, 0, 0, 0);
+      }
+      if (cr == 0) {
+        mbar_wait(&bars[0], 0);
+        if (mode != 10) mbar_wait_cluster(&bars[2], 0);
+        tc_fence_after();
+        const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+        if (mode == 10) {
+          for (int kb = 0; kb < 8; ++kb)
+            umma2_ss(tmem_base, umma_smem_desc(sA_u + (kb >> 2) * 16384 + (kb & 3) * 32, 16, 1024),
+                     umma_smem_desc(sB_u + (kb >> 2) * 8192 + (kb & 3) * 32, 16, 1024), umma_idesc(BF16, 256, 128, false, false), kb > 0);
+        } else if (mode == 11) {
+          for (int kb = 0; kb < 16; ++kb)
+            umma2_ss(tmem_base, umma_smem_desc(sA_u + kb * 2048, 16384, 1024), umma_smem_desc(sB_u + kb * 2048, 16384, 1024),
+                     umma_idesc(BF16, 128, 128, true, true), kb > 0);
+        } else {
+          for (int kb = 0; kb < 8; ++kb)
+            umma2_ts(tmem_base, tmem_base + 256 + kb * 8, umma_smem_desc(sB_u + kb * 2048, 16384, 1024),
+                     umma_idesc(BF16, 256, 128, false, true), kb > 0);
+        }
+        tc_commit_pair(&bars[1]);
+      }
+    }
+  } else {
+    const int r = threadIdx.x;   // 0..127
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t ready_bar = mapa_shared(smem_u32(&bars[2]), 0);
+    if (mode == 11) {
+      const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)(128 * cr + r) * 128);
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) {
+        const uint4 v = src[ch];
+        const uint32_t dst_cta = ch >> 3;                                   // q half -> owning CTA
+        const uint32_t off = (128 * cr + r) * 128 + (((ch & 7) ^ (r & 7)) << 4);
+        if (dst_cta == cr) *reinterpret_cast<uint4*>(sA + off) = v;
+        else st_cluster_v4(mapa_shared(smem_u32(sA) + off, dst_cta), v.x, v.y, v.z, v.w);
+      }
+      fence_proxy_async_all();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(ready_bar);
+    } else if (mode == 12) {
+      uint32_t a[64];
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(x + (size_t)(128 * cr + r) * 128);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) a[i] = src[i];
+      tmem_st_x32(tmem_base + lane_off + 256, a);
+      tmem_st_x32(tmem_base + lane_off + 256 + 32, a + 32);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(ready_bar);
+    }
+    mbar_wait(&bars[1], 0);
+    tc_fence_after();
+    if (mode == 11) {
+      uint32_t v[64];
+      tmem_ld_x32(tmem_base + lane_off, v);
+      tmem_ld_x32(tmem_base + lane_off + 32, v + 32);
+      tmem_wait_ld();
+      const int row = 64 * cr + 32 * (warp & 1) + lane, col0 = 64 * (warp >> 1);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) c[row * 128 + col0 + i] = __uint_as_float(v[i]);
+    } else {
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_base + lane_off + cb * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) c[(128 * cr + r) * 128 + cb * 32 + i] = __uint_as_float(v[i]);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair<512>(tmem_base);
+}
+
 }  // namespace
+
+cudaError_t launch_probe_pair(int mode, bool bf16, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& ty64,
+                              const void* x, float* c, cudaStream_t stream) {
+  constexpr int smem = 1024 + 65536 + 64;
+  cudaError_t e;
+  if (bf16) {
+    e = cudaFuncSetAttribute(fasn_probe_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    fasn_probe_pair_kernel<true><<<2, 160, smem, stream>>>(tx, ty, ty64, mode, reinterpret_cast<const uint16_t*>(x), c);
+  } else {
+    e = cudaFuncSetAttribute(fasn_probe_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    fasn_probe_pair_kernel<false><<<2, 160, smem, stream>>>(tx, ty, ty64, mode, reinterpret_cast<const uint16_t*>(x), c);
+  }
+  return cudaGetLastError();
+}
 
 cudaError_t launch_dropout_mask(uint8_t* out, int B, int H, int Sq, int Skv, uint32_t thr, PhiloxKey key,
                                 uint32_t bh_offset, cudaStream_t stream) {

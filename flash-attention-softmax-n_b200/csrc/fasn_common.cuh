@@ -69,6 +69,8 @@ cudaError_t launch_bwd_finish(int head_dim, bool bf16, const TensorView& dq, con
 
 cudaError_t launch_dropout_mask(uint8_t* out, int B, int H, int Sq, int Skv, uint32_t thr, PhiloxKey key,
                                 uint32_t bh_offset, cudaStream_t stream);
+cudaError_t launch_probe_pair(int mode, bool bf16, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& ty64,
+                              const void* x, float* c, cudaStream_t stream);
 cudaError_t launch_probe(int mode, bool bf16, const CUtensorMap& tx, const CUtensorMap& ty, const void* x, float* c,
                          cudaStream_t stream);
 

@@ -314,6 +314,100 @@ FASN_DEVICE void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA pairs (cluster of two, tcgen05 cta_group::2).  Shared-memory addresses in the shared::cluster window are
+// (cta rank << 24) | offset; clearing bit 24 of a local address names the same offset in CTA 0 (the leader).
+// ------------------------------------------------------------------------------------------------
+FASN_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+FASN_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+FASN_DEVICE uint32_t mapa_shared(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+FASN_DEVICE void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// arrive (release at cluster scope) on an mbarrier given by its shared::cluster address (may live in the peer CTA)
+FASN_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+FASN_DEVICE bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+// wait on a local mbarrier whose arrivals may come from the peer CTA (acquire at cluster scope)
+FASN_DEVICE void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+#ifndef FASN_NO_WATCHDOG
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > FASN_WATCHDOG_POLLS) { __trap(); }
+  }
+#else
+  while (!mbar_try_wait_cluster(bar, parity)) {}
+#endif
+}
+FASN_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+// 4-D tiled load into THIS CTA's shared memory whose completion bytes are counted on the LEADER CTA's mbarrier
+// (same offset in CTA 0): both CTAs of a pair feed one barrier that the single MMA-issuing thread waits on.
+FASN_DEVICE void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+template <uint32_t COLS> FASN_DEVICE void tmem_alloc_pair(uint32_t* smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_result)), "n"(COLS)
+               : "memory");
+}
+FASN_DEVICE void tmem_relinquish_pair() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory"); }
+template <uint32_t COLS> FASN_DEVICE void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// All previously issued cta_group::2 MMAs of this thread arrive (once) on the mbarrier at this offset in BOTH CTAs.
+FASN_DEVICE void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// cta_group::2 MMAs: D rows [0,128) live in CTA 0's TMEM, [128,256) in CTA 1's (M = 256); with M = 128 each CTA holds
+// 64 rows, columns [0,N/2) on lanes 0-63 and [N/2,N) on lanes 64-127.  A comes from each CTA's own smem / TMEM,
+// B is split along N: each CTA supplies N/2 rows from the same shared-memory offset.
+FASN_DEVICE void umma2_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+FASN_DEVICE void umma2_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // global memory helpers
 // ------------------------------------------------------------------------------------------------
 FASN_DEVICE void red_add_v4(float* gptr, float a, float b, float c, float d) {

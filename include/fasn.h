@@ -123,7 +123,11 @@ int fasn_dropout_mask(uint8_t* out, int32_t batch, int32_t heads, int32_t seqlen
  *   mode 1: C = X * Y    (A from tensor memory, B MN-major)      -- the P V form
  *   mode 2: C = X^T * Y  (A, B MN-major in shared memory)        -- the dQ = dS K form
  *   mode 3: C = X * Y    (A K-major, B MN-major in shared memory)-- the dK = dS^T Q form
- * x, y: 128x128 row-major 16-bit device arrays; c: 128x128 row-major fp32. */
+ * x, y: 128x128 row-major 16-bit device arrays; c: 128x128 row-major fp32.
+ * CTA-pair forms (cluster of two CTAs, tcgen05 cta_group::2; the paired backward kernel):
+ *   mode 10: C[256x128] = X[256x128] * Y[128x128]^T   (M = 256, B split along N between the two CTAs)
+ *   mode 11: C[128x128] = X[256x128]^T * Y[256x128]   (M = 128, K = 256, A written by local + remote stores)
+ *   mode 12: C[256x128] = X[256x128] * Y[128x128]     (M = 256, A in tensor memory) */
 int fasn_probe(int mode, uint32_t dtype, const void* x, const void* y, float* c, void* stream);
 
 /* Host-buffer convenience used for end-to-end measurement: copies q,k,v (and dout) from HOST memory,
