@@ -2,6 +2,8 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -86,13 +88,13 @@ struct DeviceGuard {
 };
 
 // (D, Sqp, B*H, 1) fp32 accumulator, box = 32 x 128 x 1 x 1 (128-byte rows), 128-byte swizzle: target of the TMA reduce-add
-int make_accum_map(CUtensorMap* m, float* ptr, long long BH, int Sqp, int D) {
+int make_accum_map(CUtensorMap* m, float* ptr, long long BH, int Sqp, int D, int box_rows = 128) {
   EncodeTiledFn fn = encode_tiled();
   if (!fn) return fail(FASN_EDRIVER, "cuTensorMapEncodeTiled is not available from this driver");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(FASN_EUNSUPPORTED, "dq_accum: pointer is not 16-byte aligned");
   cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)Sqp, (cuuint64_t)BH, 1};
   cuuint64_t strides[3] = {(cuuint64_t)D * 4, (cuuint64_t)Sqp * D * 4, (cuuint64_t)BH * Sqp * D * 4};
-  cuuint32_t box[4] = {32, 128, 1, 1};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -146,6 +148,12 @@ struct ScopedEvents {
 
 fasn::AuxView aux_view(const FasnAux& a) { return fasn::AuxView{a.ptr, a.stride_b, a.stride_h, a.stride_q}; }
 fasn::TensorView tensor_view(const FasnTensor& t) { return fasn::TensorView{t.ptr, t.stride_b, t.stride_h, t.stride_s}; }
+
+// backward main kernel: 0 = automatic, 1 = single-CTA (fasn_bwd.cu), 2 = CTA pair (fasn_bwd2.cu) where it applies
+#ifndef FASN_BWD_AUTO_PAIRED
+#define FASN_BWD_AUTO_PAIRED 0
+#endif
+std::atomic<int> g_bwd_impl{[] { const char* v = getenv("FASN_BWD_IMPL"); return (v != nullptr && v[0] >= '0' && v[0] <= '2') ? v[0] - '0' : 0; }()};
 
 uint32_t keep_threshold(float dropout_p) {
   long t = lroundf((1.0f - dropout_p) * 256.0f);
@@ -267,14 +275,32 @@ int fasn_bwd(const FasnParams* p) {
   cudaStream_t st = (cudaStream_t)p->stream;
   cudaError_t e = fasn::launch_bwd_prep(D, bf16, tensor_view(p->o), tensor_view(p->dout), a, st);
   if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd prep launch");
+  // Main kernel: the CTA-pair kernel (fasn_bwd2.cu) for head dim 128 without dense mask / bias, else the single-CTA
+  // kernel.  FASN_BWD_IMPL=1 in the environment forces the single-CTA kernel (A/B measurements, parity tests of both).
+  const int impl = g_bwd_impl.load();
+  const bool paired = (impl == 2 || (impl == 0 && FASN_BWD_AUTO_PAIRED)) && D == 128 && p->mask.ptr == nullptr && p->bias.ptr == nullptr;
+  CUtensorMap tq64, tdo64, tdq64;
+  if (paired) {
+    if (int rc = make_map(&tq64, p->q.ptr, p->q.stride_b, p->q.stride_h, p->q.stride_s, B, H, L, D, bf16, "q", 64)) return rc;
+    if (int rc = make_map(&tdo64, p->dout.ptr, p->dout.stride_b, p->dout.stride_h, p->dout.stride_s, B, H, L, D, bf16, "dout", 64)) return rc;
+    if (int rc = make_accum_map(&tdq64, p->dq_accum, (long long)B * H, (L + 127) / 128 * 128, D, 64)) return rc;
+  }
   {
     ScopedEvents prof(g_prof.bwd, st);
-    e = fasn::launch_bwd(D, bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tk, tv, tdo, tdk, tdv, tdq, a, tensor_view(p->dk), tensor_view(p->dv), st);
+    if (paired)
+      e = fasn::launch_bwd2(bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tq64, tk, tv, tdo, tdo64, tdk, tdv, tdq64, a, tensor_view(p->dk), tensor_view(p->dv), st);
+    else
+      e = fasn::launch_bwd(D, bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tk, tv, tdo, tdk, tdv, tdq, a, tensor_view(p->dk), tensor_view(p->dv), st);
   }
   if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd main launch");
   e = fasn::launch_bwd_finish(D, bf16, tensor_view(p->dq), a, st);
   if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd finish launch");
   return 0;
+}
+
+int fasn_set_bwd_impl(int impl) {
+  if (impl < 0 || impl > 2) return fail(FASN_EINVAL, "fasn_set_bwd_impl: impl must be 0 (automatic), 1 (single-CTA kernel) or 2 (CTA-pair kernel)");
+  return g_bwd_impl.exchange(impl);
 }
 
 int fasn_profile(int enable) {

@@ -65,6 +65,11 @@ cudaError_t launch_bwd(int head_dim, bool bf16, bool causal, bool dropout, const
                        const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
                        const CUtensorMap& tdq_accum, const BwdArgs& a, const TensorView& dk, const TensorView& dv,
                        cudaStream_t stream);
+// paired (2-CTA) backward main kernel: head dim 128, no dense mask / bias (fasn_bwd2.cu)
+cudaError_t launch_bwd2(bool bf16, bool causal, bool dropout, const CUtensorMap& tq, const CUtensorMap& tq64, const CUtensorMap& tk,
+                        const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdo64, const CUtensorMap& tdk,
+                        const CUtensorMap& tdv, const CUtensorMap& tdq64, const BwdArgs& a, const TensorView& dk, const TensorView& dv,
+                        cudaStream_t stream);
 cudaError_t launch_bwd_finish(int head_dim, bool bf16, const TensorView& dq, const BwdArgs& a, cudaStream_t stream);
 
 cudaError_t launch_dropout_mask(uint8_t* out, int B, int H, int Sq, int Skv, uint32_t thr, PhiloxKey key,

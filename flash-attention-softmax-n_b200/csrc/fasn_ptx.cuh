@@ -339,6 +339,12 @@ FASN_DEVICE void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, ui
 FASN_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
+// The same without cluster-scope release (the form CUTLASS's ClusterBarrier uses).  A release at cluster scope costs a
+// cluster-level memory barrier per arrive (~1000+ cycles under load, measured in the paired backward); when everything
+// the arrive publishes is ordered by tcgen05 fences / proxy fences into the CTA's own memories, CTA scope is enough.
+FASN_DEVICE void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
 FASN_DEVICE bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

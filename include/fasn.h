@@ -111,6 +111,12 @@ int fasn_bwd_workspace(const FasnParams* p, uint64_t* delta_bytes, uint64_t* dq_
  * fasn_profile_read returns the summed durations (ms) and launch counts since the last read and clears them;
  * the caller must have synchronised the stream(s) first. */
 int fasn_profile(int enable);
+
+/* Backward main-kernel selection (process-wide): 0 = automatic (whichever is faster for the shape), 1 = the single-CTA
+ * kernel (csrc/fasn_bwd.cu), 2 = the CTA-pair kernel (csrc/fasn_bwd2.cu) wherever it applies (head dim 128 without dense
+ * mask / bias; other shapes still take the single-CTA kernel).  The environment variable FASN_BWD_IMPL sets the
+ * initial value.  Returns the previous setting, or FASN_EINVAL. */
+int fasn_set_bwd_impl(int impl);
 int fasn_profile_read(double* fwd_ms, int32_t* fwd_launches, double* bwd_ms, int32_t* bwd_launches);
 
 /* Test hook: write the dropout keep mask the kernels use, as (B,H,L,S) uint8 (1 = keep), to `out`. */
