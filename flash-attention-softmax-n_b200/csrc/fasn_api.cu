@@ -209,6 +209,7 @@ int fasn_fwd(const FasnParams* p) {
   a.inv_keep = 1.0f / (1.0f - p->dropout_p);
   a.key = fasn::make_philox_key(p->philox_seed, p->philox_offset, a.drop_thr);
   a.bh_offset = (uint32_t)p->bh_offset;
+  a.sched_group = fasn::sched_group_size(2ll * D * (2ll * L + 2ll * S));            // Q, O, K, V of one unit
 #ifdef FASN_TIMELINE
   {
     extern unsigned long long* g_fasn_timeline_fwd; extern unsigned int g_fasn_timeline_fwd_xy[2];
@@ -266,6 +267,7 @@ int fasn_bwd(const FasnParams* p) {
   a.inv_keep = 1.0f / (1.0f - p->dropout_p);
   a.key = fasn::make_philox_key(p->philox_seed, p->philox_offset, a.drop_thr);
   a.bh_offset = (uint32_t)p->bh_offset;
+  a.sched_group = fasn::sched_group_size(2ll * D * (2ll * L + 2ll * S) + 4ll * D * L);   // Q, dO, K, V + the fp32 dQ accumulator
 #ifdef FASN_TIMELINE
   {
     extern unsigned long long* g_fasn_timeline; extern unsigned int g_fasn_timeline_xy[2];

@@ -32,7 +32,7 @@ namespace {
 // Optional phase timeline (compile with -DFASN_TIMELINE): one CTA records clock64() at its pipeline events into
 // BwdArgs.dbg, [role][slot] = (tag << 48) | clock.  Used by scripts/timeline.py; compiled out of the product build.
 #ifdef FASN_TIMELINE
-#define TL_DECL(role) unsigned long long* tl_p = (a.dbg && blockIdx.x == a.dbg_x && blockIdx.y == a.dbg_y) ? a.dbg + (role) * 2048 : nullptr; int tl_i = 0;
+#define TL_DECL(role) unsigned long long* tl_p = (a.dbg && kt == (int)a.dbg_x && bh == (int)a.dbg_y) ? a.dbg + (role) * 2048 : nullptr; int tl_i = 0;
 #define TL_ONLY(cond) do { if (!(cond)) tl_p = nullptr; } while (0)
 #define TL(tag) do { if (tl_p && tl_i < 2048) tl_p[tl_i++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
 #else
@@ -84,9 +84,10 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int kt = blockIdx.x;
+  const TileCoord tcd = decode_block(blockIdx.x, (a.Skv + 127) >> 7, a.B * a.H, a.sched_group);
+  const int kt = tcd.tile;
   const int k0 = kt * 128;
-  const int bh = blockIdx.y;
+  const int bh = tcd.bh;
   const int b = bh / a.H;
   const int h = bh - b * a.H;
   const int hk = (a.Hkv == 1) ? 0 : h;
@@ -536,7 +537,7 @@ static cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, co
   constexpr int smem = BwdCfg<D>::SMEM_BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  dim3 grid((a.Skv + 127) / 128, a.B * a.H, 1);
+  dim3 grid(((a.Skv + 127) / 128) * a.B * a.H, 1, 1);
   kern<<<grid, kBwdThreads, smem, stream>>>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv);
   return cudaGetLastError();
 }

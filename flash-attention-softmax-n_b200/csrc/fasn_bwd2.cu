@@ -35,7 +35,7 @@ namespace {
 
 // Optional phase timeline (compile with -DFASN_TIMELINE; same tags as fasn_bwd.cu, scripts/timeline.py)
 #ifdef FASN_TIMELINE
-#define TL_DECL(role) unsigned long long* tl_p = (a.dbg && blockIdx.x == a.dbg_x && blockIdx.y == a.dbg_y) ? a.dbg + (role) * 2048 : nullptr; int tl_i = 0;
+#define TL_DECL(role) unsigned long long* tl_p = (a.dbg && kt == (int)a.dbg_x && bh == (int)a.dbg_y) ? a.dbg + (role) * 2048 : nullptr; int tl_i = 0;
 #define TL_ONLY(cond) do { if (!(cond)) tl_p = nullptr; } while (0)
 #define TL(tag) do { if (tl_p && tl_i < 2048) tl_p[tl_i++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
 #else
@@ -109,10 +109,11 @@ fasn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t cr = cluster_ctarank();              // 0 = leader; equals blockIdx.x & 1
-  const int kt = blockIdx.x;
+  const TileCoord tcd = decode_block(blockIdx.x >> 1, (((a.Skv + 127) >> 7) + 1) >> 1, a.B * a.H, a.sched_group);   // tile = K/V tile pair
+  const int kt = 2 * tcd.tile + (int)cr;
   const int k0 = kt * 128;                            // first key of this CTA's tile
   const int k0p = (kt & ~1) * 128;                    // first key of the pair
-  const int bh = blockIdx.y;
+  const int bh = tcd.bh;
   const int b = bh / a.H;
   const int h = bh - b * a.H;
   const int hk = (a.Hkv == 1) ? 0 : h;
@@ -611,7 +612,7 @@ static cudaError_t launch_bwd2_t(const CUtensorMap& tq, const CUtensorMap& tq64,
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   const int nkv = (a.Skv + 127) / 128;
-  dim3 grid(2 * ((nkv + 1) / 2), a.B * a.H, 1);      // CTA pairs along x (static cluster dims 2 x 1 x 1)
+  dim3 grid(2 * ((nkv + 1) / 2) * a.B * a.H, 1, 1);  // CTA pairs along x (static cluster dims 2 x 1 x 1)
   kern<<<grid, kBwd2Threads, smem, stream>>>(tq, tq64, tk, tv, tdo, tdo64, tdk, tdv, tdq64, a, dk, dv);
   return cudaGetLastError();
 }

@@ -32,6 +32,7 @@ struct FwdArgs {
   float inv_keep;         // 1/(1-p)
   PhiloxKey key;
   uint32_t bh_offset;
+  int sched_group;        // units scheduled tile-major at the end of the launch (decode_block)
   unsigned long long* dbg;   // FASN_TIMELINE builds only
   unsigned int dbg_x, dbg_y;
 };
@@ -51,9 +52,38 @@ struct BwdArgs {
   float keep_prob;        // 1-p
   PhiloxKey key;
   uint32_t bh_offset;
+  int sched_group;        // units scheduled tile-major at the end of the launch (decode_block)
   unsigned long long* dbg;   // FASN_TIMELINE builds only: phase timeline buffer (see fasn_bwd.cu)
   unsigned int dbg_x, dbg_y;
 };
+
+// Work order of the tensor-core kernels.  The grid is one-dimensional; CTA `lin` works on tile `tile` of unit `bh`.
+// Units are taken one after the other with all their tiles adjacent (tiles of a unit start together and stream the same
+// K/V or Q/dO tiles in lockstep, so one DRAM fetch serves them all through L2) -- except for the last `tail` units, which
+// are taken tile-major: with a causal mask the work per tile falls with the tile index (heavy tiles are numbered first),
+// so the launch ends with the lightest tiles of many units instead of the heaviest tiles of the last unit.
+// List-scheduling simulation at S=4096 on 148 SMs: 3.5 % of the backward and 5 % of the forward; measured 7 % on the
+// C3 forward.  `tail` is sized on the host so that the tail's operands stay within ~96 MB (1..32 units).
+struct TileCoord { int tile, bh; };
+__device__ __forceinline__ TileCoord decode_block(uint32_t lin, int ntiles, int BH, int tail) {
+  tail = min(tail, BH);
+  const uint32_t head = (uint32_t)(BH - tail) * (uint32_t)ntiles;
+  TileCoord c;
+  if (lin < head) {
+    c.bh = (int)(lin / (uint32_t)ntiles);
+    c.tile = (int)(lin - (uint32_t)c.bh * (uint32_t)ntiles);
+  } else {
+    const uint32_t rem = lin - head;
+    c.tile = (int)(rem / (uint32_t)tail);
+    c.bh = (BH - tail) + (int)(rem - (uint32_t)c.tile * (uint32_t)tail);
+  }
+  return c;
+}
+
+inline int sched_group_size(long long unit_bytes) {
+  long long g = (96ll << 20) / (unit_bytes > 0 ? unit_bytes : 1);
+  return (int)(g < 1 ? 1 : (g > 32 ? 32 : g));
+}
 
 // launchers implemented in the kernel translation units
 cudaError_t launch_fwd(int head_dim, bool bf16, bool causal, bool dropout, const CUtensorMap& tq, const CUtensorMap& tk,

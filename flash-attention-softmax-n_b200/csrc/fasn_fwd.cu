@@ -30,7 +30,7 @@ namespace {
 
 // Optional phase timeline (compile with -DFASN_TIMELINE; see fasn_bwd.cu / scripts/timeline.py)
 #ifdef FASN_TIMELINE
-#define TLF_DECL(role) unsigned long long* tl_p = (a.dbg && blockIdx.x == a.dbg_x && blockIdx.y == a.dbg_y) ? a.dbg + (role) * 2048 : nullptr; int tl_i = 0;
+#define TLF_DECL(role) unsigned long long* tl_p = (a.dbg && tc.tile == (int)a.dbg_x && bh == (int)a.dbg_y) ? a.dbg + (role) * 2048 : nullptr; int tl_i = 0;
 #define TLF_ONLY(cond) do { if (!(cond)) tl_p = nullptr; } while (0)
 #define TLF(tag) do { if (tl_p && tl_i < 2048) tl_p[tl_i++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
 #else
@@ -69,9 +69,11 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qb = CAUSAL ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;   // heavy causal blocks first
+  const int nqb = (a.Sq + 255) >> 8;
+  const TileCoord tc = decode_block(blockIdx.x, nqb, a.B * a.H, a.sched_group);
+  const int qb = CAUSAL ? (nqb - 1 - tc.tile) : tc.tile;   // heavy causal blocks first
   const int q0 = qb * 256;
-  const int bh = blockIdx.y;
+  const int bh = tc.bh;
   const int b = bh / a.H;
   const int h = bh - b * a.H;
   const int hk = (a.Hkv == 1) ? 0 : h;
@@ -501,7 +503,7 @@ static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, co
   constexpr int smem = FwdCfg<D>::SMEM_BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  dim3 grid((a.Sq + 255) / 256, a.B * a.H, 1);
+  dim3 grid(((a.Sq + 255) / 256) * a.B * a.H, 1, 1);
   kern<<<grid, kFwdThreads, smem, stream>>>(tq, tk, tv, to, a);
   return cudaGetLastError();
 }

@@ -12,6 +12,10 @@
 #pragma once
 #include <cstdint>
 
+#ifndef FASN_PHILOX_ROUNDS
+#define FASN_PHILOX_ROUNDS 10
+#endif
+
 namespace fasn {
 
 struct PhiloxKey {
@@ -37,7 +41,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
                                               uint32_t (&out)[4]) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < FASN_PHILOX_ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
     const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
     c0 = hi1 ^ c1 ^ key.rk0[r];
