@@ -249,6 +249,9 @@ int fasn_bwd(const FasnParams* p) {
   if (int rc = make_map(&tdk, p->dk.ptr, p->dk.stride_b, p->dk.stride_h, p->dk.stride_s, B, H, S, D, bf16, "dk")) return rc;
   if (int rc = make_map(&tdv, p->dv.ptr, p->dv.stride_b, p->dv.stride_h, p->dv.stride_s, B, H, S, D, bf16, "dv")) return rc;
   if (p->o.ptr == nullptr) return fail(FASN_EINVAL, "o is null");
+  // the delta pre-pass reads O and dO with 16-byte loads
+  if ((reinterpret_cast<uintptr_t>(p->o.ptr) & 15) != 0 || (p->o.stride_s % 8) != 0 || (p->o.stride_h % 8) != 0 || (p->o.stride_b % 8) != 0)
+    return fail(FASN_EUNSUPPORTED, "o: pointer must be 16-byte aligned and strides multiples of 8 elements");
   CUtensorMap tdq;
   if (int rc = make_accum_map(&tdq, p->dq_accum, (long long)B * H, (L + 127) / 128 * 128, D)) return rc;
   fasn::BwdArgs a{};

@@ -14,45 +14,60 @@ namespace {
 template <int D, bool BF16>
 __global__ void __launch_bounds__(256)
 fasn_bwd_prep_kernel(TensorView o, TensorView dout, BwdArgs a) {
-  // one warp per (bh, row); rows in [Sq, Sqp) are padding and get delta = 0
+  // D / 8 lanes per (bh, row), 16-byte loads of O and dO (8 elements per lane), four rows per group of lanes in flight;
+  // rows in [Sq, Sqp) are padding and get delta = 0.  HBM-bound: 2 x 2 D bytes read + 4 D bytes of zero-fill per row.
+  constexpr int LPR = D / 8;                 // lanes per row: 16 (D=128) or 8 (D=64)
+  constexpr int RPW = 32 / LPR;              // rows per warp pass
+  constexpr int PASSES = 4;
   const int lane = threadIdx.x & 31;
-  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int sub = lane / LPR, l = lane % LPR;
   const long long total = (long long)a.B * a.H * a.Sqp;
-  if (warp_global >= total) return;
-  const int row = (int)(warp_global % a.Sqp);
-  const int bh = (int)(warp_global / a.Sqp);
-  const int b = bh / a.H, h = bh - b * a.H;
-  float acc = 0.f;
-  if (row < a.Sq) {
-    const uint16_t* po = reinterpret_cast<const uint16_t*>(o.ptr) + b * o.sb + h * o.sh + (long long)row * o.ss;
-    const uint16_t* pd = reinterpret_cast<const uint16_t*>(dout.ptr) + b * dout.sb + h * dout.sh + (long long)row * dout.ss;
-    constexpr int PER = D / 32;   // elements per lane: 4 (D=128) or 2 (D=64)
-    if constexpr (PER == 4) {
-      const uint2 vo = *reinterpret_cast<const uint2*>(po + lane * 4);
-      const uint2 vd = *reinterpret_cast<const uint2*>(pd + lane * 4);
-      acc += cvt16_to_f32<BF16>(vo.x & 0xFFFF) * cvt16_to_f32<BF16>(vd.x & 0xFFFF);
-      acc += cvt16_to_f32<BF16>(vo.x >> 16) * cvt16_to_f32<BF16>(vd.x >> 16);
-      acc += cvt16_to_f32<BF16>(vo.y & 0xFFFF) * cvt16_to_f32<BF16>(vd.y & 0xFFFF);
-      acc += cvt16_to_f32<BF16>(vo.y >> 16) * cvt16_to_f32<BF16>(vd.y >> 16);
-    } else {
-      const uint32_t vo = *reinterpret_cast<const uint32_t*>(po + lane * 2);
-      const uint32_t vd = *reinterpret_cast<const uint32_t*>(pd + lane * 2);
-      acc += cvt16_to_f32<BF16>(vo & 0xFFFF) * cvt16_to_f32<BF16>(vd & 0xFFFF);
-      acc += cvt16_to_f32<BF16>(vo >> 16) * cvt16_to_f32<BF16>(vd >> 16);
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long row0 = warp_global * (RPW * PASSES) + sub;
+  uint4 vo[PASSES], vd[PASSES];
+  bool live[PASSES];
+#pragma unroll
+  for (int p = 0; p < PASSES; ++p) {
+    const long long rg = row0 + p * RPW;
+    live[p] = false;
+    vo[p] = make_uint4(0, 0, 0, 0); vd[p] = make_uint4(0, 0, 0, 0);
+    if (rg < total) {
+      const int row = (int)(rg % a.Sqp);
+      const int bh = (int)(rg / a.Sqp);
+      const int b = bh / a.H, h = bh - b * a.H;
+      if (row < a.Sq) {
+        live[p] = true;
+        vo[p] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(o.ptr) + b * o.sb + h * o.sh + (long long)row * o.ss) + l);
+        vd[p] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(dout.ptr) + b * dout.sb + h * dout.sh + (long long)row * dout.ss) + l);
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < PASSES; ++p) {
+    const long long rg = row0 + p * RPW;
+    const uint32_t wo[4] = {vo[p].x, vo[p].y, vo[p].z, vo[p].w}, wd[4] = {vd[p].x, vd[p].y, vd[p].z, vd[p].w};
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc = fmaf(cvt16_to_f32<BF16>(wo[e] & 0xFFFF), cvt16_to_f32<BF16>(wd[e] & 0xFFFF), acc);
+      acc = fmaf(cvt16_to_f32<BF16>(wo[e] >> 16), cvt16_to_f32<BF16>(wd[e] >> 16), acc);
     }
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    for (int sft = LPR / 2; sft > 0; sft >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, sft);
+    if (rg < total) {
+      const int row = (int)(rg % a.Sqp);
+      const int bh = (int)(rg / a.Sqp);
+      if (l == 0) {
+        float* ws = const_cast<float*>(a.delta);
+        ws[rg] = live[p] ? acc * a.keep_prob : 0.f;      // (1-p) delta: see the dS' formulation in fasn_bwd.cu
+        // second half of the workspace: LSE_n in the log2 domain, +inf on padding rows (=> P = 0 there)
+        ws[total + rg] = live[p] ? a.lse[(long long)bh * a.Sq + row] * kLog2e : INFINITY;
+      }
+      float4* acc_row = reinterpret_cast<float4*>(a.dq_accum + rg * D);   // D fp32 per row = 2 float4 per lane
+      acc_row[l * 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+      acc_row[l * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
-  if (lane == 0) {
-    float* ws = const_cast<float*>(a.delta);
-    ws[(long long)bh * a.Sqp + row] = acc * a.keep_prob;    // (1-p) delta: see the dS' formulation in fasn_bwd.cu
-    // second half of the workspace: LSE_n in the log2 domain, +inf on padding rows (=> P = 0 there)
-    ws[(long long)a.B * a.H * a.Sqp + (long long)bh * a.Sqp + row] =
-        (row < a.Sq) ? a.lse[(long long)bh * a.Sq + row] * kLog2e : INFINITY;
-  }
-  float* acc_row = a.dq_accum + ((long long)bh * a.Sqp + row) * D;
-  if constexpr (D == 128) reinterpret_cast<float4*>(acc_row)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-  else                    reinterpret_cast<float2*>(acc_row)[lane] = make_float2(0.f, 0.f);
 }
 
 template <int D, bool BF16>
@@ -83,7 +98,9 @@ fasn_bwd_finish_kernel(TensorView dq, BwdArgs a) {
 
 cudaError_t launch_bwd_prep(int head_dim, bool bf16, const TensorView& o, const TensorView& dout, const BwdArgs& a,
                             cudaStream_t stream) {
-  const long long warps = (long long)a.B * a.H * a.Sqp;
+  const long long rows = (long long)a.B * a.H * a.Sqp;
+  const int rows_per_warp = (32 / (head_dim / 8)) * 4;
+  const long long warps = (rows + rows_per_warp - 1) / rows_per_warp;
   const int blocks = (int)((warps + 7) / 8);
   if (head_dim == 128 && bf16) fasn_bwd_prep_kernel<128, true><<<blocks, 256, 0, stream>>>(o, dout, a);
   else if (head_dim == 128) fasn_bwd_prep_kernel<128, false><<<blocks, 256, 0, stream>>>(o, dout, a);
