@@ -331,15 +331,20 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int r = quarter * 32 + lane;                     // kv row inside the tile
     const int kv_row = k0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const bool kv_valid = kv_row < a.Skv;
-    const bool has_aux = (a.mask.ptr != nullptr) || (a.bias.ptr != nullptr);
     const int kv_c = min(kv_row, a.Skv - 1);
     const uint8_t* mbase = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr) + b * a.mask.sb + h * a.mask.sh + kv_c : nullptr;
+    // A mask that is broadcast over the query axis (key padding, (B|1, H|1, 1, S)) is one byte per key: this thread's
+    // key is either visible to every query or to none, which the fast path handles like a row beyond Skv.
+    const bool key_only_mask = (mbase != nullptr) && (a.mask.sq == 0);
+    const bool key_masked = key_only_mask && (*mbase == 0);
+    if (key_only_mask) mbase = nullptr;
+    const bool kv_valid = (kv_row < a.Skv) && !key_masked;
+    const bool has_aux = (mbase != nullptr) || (a.bias.ptr != nullptr);
     const uint16_t* bbase = a.bias.ptr ? reinterpret_cast<const uint16_t*>(a.bias.ptr) + b * a.bias.sb + h * a.bias.sh + kv_c : nullptr;
     const uint32_t bh_global = a.bh_offset + bh;
     const uint32_t kvw = (uint32_t)(kv_row >> 5);          // identical for the 32 lanes of this warp
 
-    const bool kv_tail = (k0 + 128 > a.Skv);               // this K/V tile has rows beyond Skv
+    const bool kv_tail = (k0 + 128 > a.Skv) || key_only_mask;   // this K/V tile (may) have rows that no query sees
     TL_DECL(1 + half)
     TL_ONLY(threadIdx.x == 0 || threadIdx.x == 128);
     const float2 c2 = make_float2(a.scale_log2, a.scale_log2);

@@ -282,7 +282,11 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int n_t = (t == 0) ? n_tiles0 : n_tiles1;      // K/V tiles this Q tile needs
     // Fast path: the logit scale is folded into the exponent FFMA (p = 2^(s*c - m)) and the running max is taken on
     // the raw scores (valid for c > 0).  Generic path (mask / bias / non-positive scale): scores are scaled first.
-    const bool generic = has_aux || !(a.scale_log2 > 0.f);
+    // A mask broadcast over the query axis (key padding, row stride 0) without bias stays on the fast path: the 128 mask
+    // bytes of a K/V tile are the same for every row, so each warp turns them into four 32-bit visibility words with
+    // ballots and only tiles that contain a hidden key pay for the selects.
+    const bool key_only_mask = (mrow != nullptr) && (a.mask.sq == 0) && (brow == nullptr) && (a.scale_log2 > 0.f);
+    const bool generic = (has_aux && !key_only_mask) || !(a.scale_log2 > 0.f);
     const float cmul = generic ? 1.f : a.scale_log2;
     const float2 cmul2 = make_float2(cmul, cmul);
 
@@ -299,6 +303,16 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 4; ++i) kw[i] = dropout_keep_word(a.key, bh_global, (uint32_t)row, (uint32_t)(j0 >> 5) + i, a.drop_thr);
       }
+      uint32_t vis[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+      if (key_only_mask) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int col = j0 + 32 * i + lane;
+          const uint8_t mb = (col < a.Skv) ? __ldg(mrow + col) : (uint8_t)1;      // keys beyond Skv are cut by row_lim below
+          vis[i] = __ballot_sync(0xffffffffu, mb != 0);
+        }
+      }
+      const bool hidden_keys = (vis[0] & vis[1] & vis[2] & vis[3]) != 0xFFFFFFFFu;   // warp-uniform
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       float s[128];
@@ -358,11 +372,15 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
       }
-      const bool masked_tile = (j0 + 128 > warp_row_lim);      // warp-uniform
-      if (masked_tile) {
+      const bool masked_tile = (j0 + 128 > warp_row_lim) || hidden_keys;      // warp-uniform
+      if (j0 + 128 > warp_row_lim) {
         const int lim = row_lim - j0;
 #pragma unroll
         for (int c = 0; c < 128; ++c) s[c] = (c < lim) ? s[c] : -INFINITY;
+      }
+      if (hidden_keys) {
+#pragma unroll
+        for (int c = 0; c < 128; ++c) s[c] = ((vis[c >> 5] >> (c & 31)) & 1u) ? s[c] : -INFINITY;
       }
       float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll

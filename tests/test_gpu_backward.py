@@ -17,6 +17,8 @@ CASES = [
     (2, 1, 96, 160, 64, 0.5, True, None),        # S > L causal
     (1, 1, 640, 640, 128, 1e-3, True, None),
     (6, 1, 1024, 1024, 64, 1.0, True, 0.5),      # the reference's GPU test shape (tests/gpu/core/test_flash_attn.py:16-18)
+    (5, 8, 256, 384, 128, 0.5, True, None),      # 40 units: both halves of the launch order (unit-major head, tile-major tail of 32)
+    (7, 6, 200, 200, 64, 1.0, True, None),       # 42 units, ragged
 ]
 
 
@@ -165,3 +167,26 @@ def test_large_logits_exercise_rescaling(fasn_lib, dtype, n):
         # near-one-hot softmax amplifies the rounding of the 16-bit logits themselves: judge against the reference's own
         # low-precision path rather than a fixed envelope
         assert rel <= max(2.0 * nat_rel, 3.0 * REL_L2[dtype]), f"{name}: rel-L2 {rel:.3e} vs native {nat_rel:.3e}"
+
+
+@pytest.mark.parametrize("D,causal,with_bias", [(128, True, False), (64, False, False), (128, False, True)])
+def test_backward_key_padding_mask(fasn_lib, D, causal, with_bias):
+    """(B,1,1,S) key-padding masks are broadcast over the query axis (row stride 0): the backward treats a padded key like
+    a key beyond S (fast path) unless a dense bias forces the generic path."""
+    dtype = torch.float16
+    B, H, L, S = 3, 2, 200, 300
+    q, k, v, do = make_qkv(B, H, L, S, D, dtype, seed=21)
+    lens = torch.tensor([300, 170, 64])
+    mask = (torch.arange(S)[None, :] < lens[:, None]).view(B, 1, 1, S)
+    kw = dict(softmax_n_param=1.0, is_causal=causal)
+    bias = None
+    if with_bias:
+        bias = torch.randn(H, L, S, generator=torch.Generator().manual_seed(5)).to(dtype)
+    got = run_fused(q, k, v, do, attn_mask=mask.cuda(), attn_bias=None if bias is None else bias.cuda(), **kw)
+    want = oracle_all(q, k, v, do, attn_mask=mask, attn_bias=None if bias is None else bias.double(), **kw)
+    for name, a, b in zip(("O", "dQ", "dK", "dV"), got, want):
+        check_close(name + "(key padding)", a, b, None, dtype, rel_scale=1.5)
+    # gradients of padded keys are exactly zero
+    for bi, n in enumerate(lens.tolist()):
+        assert float(got[2][bi, :, n:].abs().max() if n < S else 0.0) == 0.0
+        assert float(got[3][bi, :, n:].abs().max() if n < S else 0.0) == 0.0

@@ -20,6 +20,8 @@ CASES = [
     (1, 1, 1, 77, 128, 1.0, False, None),        # single query row
     (1, 2, 1024, 1152, 64, 1e-3, True, 0.3),     # the reference's GPU analytic-test shape
     (1, 1, 640, 640, 128, 1e-6, True, None),
+    (5, 8, 512, 384, 128, 0.5, True, None),      # 40 units: both halves of the launch order (unit-major head, tile-major tail)
+    (7, 6, 300, 300, 64, 1.0, True, None),       # 42 units, ragged
 ]
 
 
