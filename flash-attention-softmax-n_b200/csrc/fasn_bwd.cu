@@ -370,6 +370,31 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t keep0 = keep_next0, keep1 = keep_next1;
       // ---- P^T = 2^(S^T c - LSE2)
       TL(10);
+      // Dense bias / mask (generic path): this thread needs one column of the (L, S) matrix -- its key, 64 queries.  The
+      // 32 lanes of a warp read 32 consecutive keys, so each load instruction is one coalesced 64-byte segment; all 64
+      // (+64) loads are independent of S^T and are issued here, before the wait for the tensor core, so their latency
+      // overlaps it.  Rows beyond Sq are clamped (their P is 0 anyway: LSE2 = +inf on padding rows).
+      uint32_t bpk[32];
+      uint32_t mb0 = 0xFFFFFFFFu, mb1 = 0xFFFFFFFFu;
+      if (has_aux) {
+        if (bbase) {
+#pragma unroll
+          for (int c = 0; c < 64; c += 2) {
+            const uint32_t lo = __ldg(bbase + (long long)min(qc0 + c, a.Sq - 1) * a.bias.sq);
+            const uint32_t hi = __ldg(bbase + (long long)min(qc0 + c + 1, a.Sq - 1) * a.bias.sq);
+            bpk[c >> 1] = lo | (hi << 16);
+          }
+        }
+        if (mbase) {
+          uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            m0 |= (__ldg(mbase + (long long)min(qc0 + c, a.Sq - 1) * a.mask.sq) != 0 ? 1u : 0u) << c;
+            m1 |= (__ldg(mbase + (long long)min(qc0 + 32 + c, a.Sq - 1) * a.mask.sq) != 0 ? 1u : 0u) << c;
+          }
+          mb0 = m0; mb1 = m1;
+        }
+      }
       mbar_wait(&q_full[s], ph);          // LSE2 and delta of this tile have landed (same barrier as Q_i)
       mbar_wait(s_full, it & 1);
       tc_fence_after();
@@ -383,30 +408,17 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       const float* lse_s = sLse + s * 128 + half * 64;
       if (has_aux) {
-        // generic path: bias added / mask applied in the log2 domain before the exponent.  This thread walks down a
-        // column of the dense (L, S) bias / mask (fixed key, 64 queries): the 32 lanes of a warp read 32 consecutive
-        // keys, so every load instruction is one coalesced segment; pointers advance by the row stride.
-        const bool full_q = (qi0 + 128 <= a.Sq);            // no query row of this tile lies beyond Sq
-        const uint16_t* bp = bbase ? bbase + (long long)min(qc0, a.Sq - 1) * a.bias.sq : nullptr;
-        const uint8_t* mp = mbase ? mbase + (long long)min(qc0, a.Sq - 1) * a.mask.sq : nullptr;
+        // generic path: bias added / mask applied in the log2 domain before the exponent
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-          float bv[16];
-          uint32_t mbits = 0xFFFFu;
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const bool in_q = full_q || (qc0 + c0 + e < a.Sq);
-            bv[e] = 0.f;
-            if (bp) { if (in_q) bv[e] = cvt16_to_f32<BF16>(*bp); bp += a.bias.sq; }
-            if (mp) { if (in_q && *mp == 0) mbits &= ~(1u << e); mp += a.mask.sq; }
-          }
-          const float4* l4p = reinterpret_cast<const float4*>(lse_s + c0);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float lse_e = reinterpret_cast<const float*>(l4p)[e];
-            float x = fmaf(p[c0 + e], a.scale_log2, bv[e] * kLog2e);
-            p[c0 + e] = ((mbits >> e) & 1u) ? ex2(x - lse_e) : 0.f;
-          }
+        for (int c = 0; c < 64; c += 2) {
+          const float2 l2 = *reinterpret_cast<const float2*>(lse_s + c);
+          float b0 = 0.f, b1 = 0.f;
+          if (bbase) { b0 = cvt16_to_f32<BF16>((uint16_t)(bpk[c >> 1] & 0xFFFF)); b1 = cvt16_to_f32<BF16>((uint16_t)(bpk[c >> 1] >> 16)); }
+          const float x0 = fmaf(p[c], a.scale_log2, b0 * kLog2e) - l2.x;
+          const float x1 = fmaf(p[c + 1], a.scale_log2, b1 * kLog2e) - l2.y;
+          const uint32_t mw = (c < 32) ? mb0 : mb1;
+          p[c] = ((mw >> (c & 31)) & 1u) ? ex2(x0) : 0.f;
+          p[c + 1] = ((mw >> ((c + 1) & 31)) & 1u) ? ex2(x1) : 0.f;
         }
       } else {
 #pragma unroll
