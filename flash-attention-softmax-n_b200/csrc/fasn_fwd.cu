@@ -57,7 +57,10 @@ template <int D> struct FwdCfg {
   static constexpr int SMEM_BYTES = 1024 + (2 + 2 * NS) * TILE_BYTES + NUM_BARS * 8 + 16;
 };
 
-template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
+// GENERIC = false: the fast path (no dense mask / bias, positive scale; a key-padding mask with row stride 0 is fine).
+// GENERIC = true:  dense attn_mask / attn_bias tensors and non-positive scales (scores are scaled before the maximum).
+// Two instantiations so that the dense-tensor code (and its registers) stays out of the kernels the headline shapes run.
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT, bool GENERIC>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const FwdArgs a) {
@@ -285,8 +288,8 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // A mask broadcast over the query axis (key padding, row stride 0) without bias stays on the fast path: the 128 mask
     // bytes of a K/V tile are the same for every row, so each warp turns them into four 32-bit visibility words with
     // ballots and only tiles that contain a hidden key pay for the selects.
-    const bool key_only_mask = (mrow != nullptr) && (a.mask.sq == 0) && (brow == nullptr) && (a.scale_log2 > 0.f);
-    const bool generic = (has_aux && !key_only_mask) || !(a.scale_log2 > 0.f);
+    const bool key_only_mask = !GENERIC && (mrow != nullptr);      // (the host picks GENERIC unless row stride 0, no bias, scale > 0)
+    constexpr bool generic = GENERIC;
     const float cmul = generic ? 1.f : a.scale_log2;
     const float2 cmul2 = make_float2(cmul, cmul);
 
@@ -313,6 +316,18 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
       const bool hidden_keys = (vis[0] & vis[1] & vis[2] & vis[3]) != 0xFFFFFFFFu;   // warp-uniform
+      // Dense bias (GENERIC kernels): this thread's 128 elements of the tile are sixteen 16-byte loads.  On interior tiles
+      // with an aligned row they are issued here, unconditionally and before the wait for the tensor core, so their
+      // latency overlaps it (conditional loads serialise: one DRAM round trip each).
+      const bool bias_fast = GENERIC && brow != nullptr && (j0 + 128 <= a.Skv) && ((reinterpret_cast<uintptr_t>(brow) & 15) == 0);
+      const bool mask_fast = GENERIC && mrow != nullptr && (j0 + 128 <= a.Skv) && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0);
+      uint4 bq[GENERIC ? 16 : 1];
+      if constexpr (GENERIC) {
+        if (bias_fast) {
+#pragma unroll
+          for (int g = 0; g < 16; ++g) bq[g] = __ldg(reinterpret_cast<const uint4*>(brow + j0) + g);
+        }
+      }
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       float s[128];
@@ -326,13 +341,23 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_wait_ld();
         TLF(12);
       }
-      if (generic) {
+      if constexpr (GENERIC) {
 #pragma unroll
         for (int c = 0; c < 128; ++c) s[c] *= a.scale_log2;
         if (has_aux) {
           // dense bias / mask rows of this thread: 16-byte loads where the row segment is aligned and in range
           // (each thread streams its own 256 B / 128 B per tile; lines are shared by consecutive instructions via L1)
-          if (brow) {
+          if (bias_fast) {
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+              const uint32_t w[4] = {bq[g].x, bq[g].y, bq[g].z, bq[g].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                s[g * 8 + 2 * e] = fmaf(cvt16_to_f32<BF16>(w[e] & 0xFFFF), kLog2e, s[g * 8 + 2 * e]);
+                s[g * 8 + 2 * e + 1] = fmaf(cvt16_to_f32<BF16>(w[e] >> 16), kLog2e, s[g * 8 + 2 * e + 1]);
+              }
+            }
+          } else if (brow) {
 #pragma unroll
             for (int g = 0; g < 16; ++g) {                    // 8 bias elements per 16-byte load
               const int col = j0 + g * 8;
@@ -352,7 +377,18 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               }
             }
           }
-          if (mrow) {
+          if (mask_fast) {
+            uint4 mq[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) mq[g] = __ldg(reinterpret_cast<const uint4*>(mrow + j0) + g);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const uint32_t w[4] = {mq[g].x, mq[g].y, mq[g].z, mq[g].w};
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (((w[e >> 2] >> (8 * (e & 3))) & 0xFF) == 0) s[g * 16 + e] = -INFINITY;
+            }
+          } else if (mrow) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {                     // 16 mask bytes per 16-byte load
               const int col = j0 + g * 16;
@@ -514,16 +550,24 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
 }  // namespace
 
-template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
-static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT, bool GENERIC>
+static cudaError_t launch_fwd_t2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
                                 const FwdArgs& a, cudaStream_t stream) {
-  auto kern = fasn_fwd_kernel<D, BF16, CAUSAL, DROPOUT>;
+  auto kern = fasn_fwd_kernel<D, BF16, CAUSAL, DROPOUT, GENERIC>;
   constexpr int smem = FwdCfg<D>::SMEM_BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   dim3 grid(((a.Sq + 255) / 256) * a.B * a.H, 1, 1);
   kern<<<grid, kFwdThreads, smem, stream>>>(tq, tk, tv, to, a);
   return cudaGetLastError();
+}
+
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
+static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
+                                const FwdArgs& a, cudaStream_t stream) {
+  const bool generic = a.bias.ptr != nullptr || (a.mask.ptr != nullptr && a.mask.sq != 0) || !(a.scale_log2 > 0.f);
+  return generic ? launch_fwd_t2<D, BF16, CAUSAL, DROPOUT, true>(tq, tk, tv, to, a, stream)
+                 : launch_fwd_t2<D, BF16, CAUSAL, DROPOUT, false>(tq, tk, tv, to, a, stream);
 }
 
 cudaError_t launch_fwd(int head_dim, bool bf16, bool causal, bool dropout, const CUtensorMap& tq, const CUtensorMap& tk,
