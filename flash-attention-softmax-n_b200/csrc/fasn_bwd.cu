@@ -71,7 +71,9 @@ FASN_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, 
                : "memory");
 }
 
-template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
+// AUX = true: dense attn_mask / attn_bias tensors (generic path); AUX = false keeps that code out of the fast kernels
+// (a key-padding mask with row stride 0 is handled by both).
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT, bool AUX>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -339,7 +341,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const bool key_masked = key_only_mask && (*mbase == 0);
     if (key_only_mask) mbase = nullptr;
     const bool kv_valid = (kv_row < a.Skv) && !key_masked;
-    const bool has_aux = (mbase != nullptr) || (a.bias.ptr != nullptr);
+    const bool has_aux = AUX && ((mbase != nullptr) || (a.bias.ptr != nullptr));
     const uint16_t* bbase = a.bias.ptr ? reinterpret_cast<const uint16_t*>(a.bias.ptr) + b * a.bias.sb + h * a.bias.sh + kv_c : nullptr;
     const uint32_t bh_global = a.bh_offset + bh;
     const uint32_t kvw = (uint32_t)(kv_row >> 5);          // identical for the 32 lanes of this warp
@@ -374,15 +376,15 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // 32 lanes of a warp read 32 consecutive keys, so each load instruction is one coalesced 64-byte segment; all 64
       // (+64) loads are independent of S^T and are issued here, before the wait for the tensor core, so their latency
       // overlaps it.  Rows beyond Sq are clamped (their P is 0 anyway: LSE2 = +inf on padding rows).
-      uint32_t bpk[32];
+      uint32_t bpk[AUX ? 32 : 1];
       uint32_t mb0 = 0xFFFFFFFFu, mb1 = 0xFFFFFFFFu;
-      if (has_aux) {
+      if constexpr (AUX) if (has_aux) {
         if (bbase) {
 #pragma unroll
           for (int c = 0; c < 64; c += 2) {
             const uint32_t lo = __ldg(bbase + (long long)min(qc0 + c, a.Sq - 1) * a.bias.sq);
             const uint32_t hi = __ldg(bbase + (long long)min(qc0 + c + 1, a.Sq - 1) * a.bias.sq);
-            bpk[c >> 1] = lo | (hi << 16);
+            bpk[AUX ? (c >> 1) : 0] = lo | (hi << 16);
           }
         }
         if (mbase) {
@@ -413,7 +415,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         for (int c = 0; c < 64; c += 2) {
           const float2 l2 = *reinterpret_cast<const float2*>(lse_s + c);
           float b0 = 0.f, b1 = 0.f;
-          if (bbase) { b0 = cvt16_to_f32<BF16>((uint16_t)(bpk[c >> 1] & 0xFFFF)); b1 = cvt16_to_f32<BF16>((uint16_t)(bpk[c >> 1] >> 16)); }
+          if (bbase) { b0 = cvt16_to_f32<BF16>((uint16_t)(bpk[AUX ? (c >> 1) : 0] & 0xFFFF)); b1 = cvt16_to_f32<BF16>((uint16_t)(bpk[AUX ? (c >> 1) : 0] >> 16)); }
           const float x0 = fmaf(p[c], a.scale_log2, b0 * kLog2e) - l2.x;
           const float x1 = fmaf(p[c + 1], a.scale_log2, b1 * kLog2e) - l2.y;
           const uint32_t mw = (c < 32) ? mb0 : mb1;
@@ -546,17 +548,26 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
 }  // namespace
 
-template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
-static cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT, bool AUX>
+static cudaError_t launch_bwd_t2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
                                 const CUtensorMap& tdk, const CUtensorMap& tdv, const CUtensorMap& tdq, const BwdArgs& a, const TensorView& dk,
                                 const TensorView& dv, cudaStream_t stream) {
-  auto kern = fasn_bwd_kernel<D, BF16, CAUSAL, DROPOUT>;
+  auto kern = fasn_bwd_kernel<D, BF16, CAUSAL, DROPOUT, AUX>;
   constexpr int smem = BwdCfg<D>::SMEM_BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   dim3 grid(((a.Skv + 127) / 128) * a.B * a.H, 1, 1);
   kern<<<grid, kBwdThreads, smem, stream>>>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv);
   return cudaGetLastError();
+}
+
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
+static cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                                const CUtensorMap& tdk, const CUtensorMap& tdv, const CUtensorMap& tdq, const BwdArgs& a, const TensorView& dk,
+                                const TensorView& dv, cudaStream_t stream) {
+  const bool aux = a.bias.ptr != nullptr || (a.mask.ptr != nullptr && a.mask.sq != 0);
+  return aux ? launch_bwd_t2<D, BF16, CAUSAL, DROPOUT, true>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv, stream)
+             : launch_bwd_t2<D, BF16, CAUSAL, DROPOUT, false>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv, stream);
 }
 
 cudaError_t launch_bwd(int head_dim, bool bf16, bool causal, bool dropout, const CUtensorMap& tq, const CUtensorMap& tk,
