@@ -140,20 +140,37 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* dq_full = bars + 14;
   uint64_t* dq_empty = bars + 15;  // 128 arrivals
   uint64_t* dkv_full = bars + 16;
+  uint64_t* dv_full = bars + 17;   // the last dV MMA has completed: the dV epilogue overlaps the last dQ / dK MMAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NUM_BARS);
 
+  const float* lse2_ws = a.delta + (long long)a.B * a.H * a.Sqp;     // second half of the workspace: LSE_n * log2e
   if (warp == 12 && lane == 0) {
+    // The producer thread initialises the barriers itself and issues the first loads (K, V, Q / LSE2 / delta / dO of the
+    // first tile) at once, before the TMEM allocation and the CTA-wide sync below: they are pure pipeline fill otherwise.
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_dk); tma_prefetch_desc(&tm_dv); tma_prefetch_desc(&tm_dq);
-  }
-  if (warp == 13 && lane == 0) {
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     mbar_init(do_full, 1); mbar_init(do_empty, 1);
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(ds_empty, 1);
-    mbar_init(dq_full, 1); mbar_init(dq_empty, 128); mbar_init(dkv_full, 1);
+    mbar_init(dq_full, 1); mbar_init(dq_empty, 128); mbar_init(dkv_full, 1); mbar_init(dv_full, 1);
     fence_mbar_init();
     fence_proxy_async_smem();
+    mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
+#pragma unroll
+    for (int db = 0; db < DB; ++db) {
+      tma_load_4d(sK + db * BLK_BYTES, &tm_k, kv_full, db * 64, k0, hk, b);
+      tma_load_4d(sV + db * BLK_BYTES, &tm_v, kv_full, db * 64, k0, hk, b);
+    }
+    const int qi0 = i_start * 128;
+    mbar_arrive_expect_tx(&q_full[0], TILE_BYTES + 1024);
+#pragma unroll
+    for (int db = 0; db < DB; ++db) tma_load_4d(sQ + db * BLK_BYTES, &tm_q, &q_full[0], db * 64, qi0, h, b);
+    bulk_load_1d(sLse, lse2_ws + (long long)bh * a.Sqp + qi0, 512, &q_full[0]);
+    bulk_load_1d(sDelta, a.delta + (long long)bh * a.Sqp + qi0, 512, &q_full[0]);
+    mbar_arrive_expect_tx(do_full, TILE_BYTES);
+#pragma unroll
+    for (int db = 0; db < DB; ++db) tma_load_4d(sDO + db * BLK_BYTES, &tm_do, do_full, db * 64, qi0, h, b);
   }
   if (warp == 14) { tmem_alloc<512>(tmem_slot); tmem_relinquish(); }
   tc_fence_before();
@@ -165,14 +182,8 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     setmaxnreg_dec<56>();
     if (warp == 12 && lane == 0) {
       // ---------------------------------------------------------------- TMA producer
-      mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
-#pragma unroll
-      for (int db = 0; db < DB; ++db) {
-        tma_load_4d(sK + db * BLK_BYTES, &tm_k, kv_full, db * 64, k0, hk, b);
-        tma_load_4d(sV + db * BLK_BYTES, &tm_v, kv_full, db * 64, k0, hk, b);
-      }
-      const float* lse2 = a.delta + (long long)a.B * a.H * a.Sqp;     // second half of the workspace
-      for (int it = 0; it < n_iter; ++it) {
+      const float* lse2 = lse2_ws;
+      for (int it = 1; it < n_iter; ++it) {     // K, V and the first Q / dO tile were issued before the CTA-wide sync
         const int s = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         const int qi0 = (i_start + it) * 128;
@@ -238,6 +249,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             umma_ts(tm + TM_DV, tm + TM_S + (kb >> 2) * 64 + (kb & 3) * 8, umma_desc_join(do_mn + kb * (2048 >> 4), hi_desc),
                     idesc_dv, (it > 0 || kb > 0) ? 1u : 0u);
           tc_commit(do_empty);         // dO_i is dead once dP^T_i (issued earlier) and dV_i have completed
+          if (!more) tc_commit(dv_full);
         }
         __syncwarp();
         // S^T of the next Q tile (overwrites P^T: ordered behind the dV MMAs on the tensor pipe)
@@ -500,11 +512,15 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
 
     // ------------------------------------------------------------------ dK, dV epilogue
-    mbar_wait(dkv_full, 0);
-    tc_fence_after();
-    // K and V tiles are dead now: stage dK into sK and dV into sV (same swizzled [block][row][128 B] layout)
+    // V is dead after the last dP^T, K after the last dQ: stage dV into sV as soon as the last dV MMA is done (the last
+    // dQ / dK MMAs are still running), then dK into sK (same swizzled [block][row][128 B] layout)
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
+#ifndef FASN_BWD_SPLIT_EPI
+#define FASN_BWD_SPLIT_EPI 1
+#endif
+      if (which == 0 && FASN_BWD_SPLIT_EPI) mbar_wait(dv_full, 0); else mbar_wait(dkv_full, 0);
+      tc_fence_after();
       uint8_t* stage = which == 0 ? sV : sK;
       const uint32_t tm_src = which == 0 ? TM_DV : TM_DK;
       const float mul = which == 0 ? (DROPOUT ? a.inv_keep : 1.f) : a.scale;   // a.scale already carries 1/(1-p)
@@ -527,18 +543,18 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           *reinterpret_cast<uint4*>(stage + db * BLK_BYTES + r * 128 + ((cc ^ (r & 7)) << 4)) = w;
         }
       }
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(1, 256);
-    if (threadIdx.x == 0) {
+      fence_proxy_async_smem();
+      named_bar_sync(1, 256);
+      if (threadIdx.x == 0) {
 #pragma unroll
-      for (int db = 0; db < DB; ++db) {
-        tma_store_4d(&tm_dv, sV + db * BLK_BYTES, db * 64, k0, h, b);
-        tma_store_4d(&tm_dk, sK + db * BLK_BYTES, db * 64, k0, h, b);
+        for (int db = 0; db < DB; ++db) {
+          if (which == 0) tma_store_4d(&tm_dv, sV + db * BLK_BYTES, db * 64, k0, h, b);
+          else            tma_store_4d(&tm_dk, sK + db * BLK_BYTES, db * 64, k0, h, b);
+        }
+        tma_store_commit();
       }
-      tma_store_commit();
-      tma_store_wait_all();
     }
+    if (threadIdx.x == 0) tma_store_wait_read_all();     // the staging tiles have been read; the global writes complete on their own
   }
 
   tc_fence_before();
