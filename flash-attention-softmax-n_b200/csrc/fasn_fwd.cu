@@ -45,6 +45,9 @@ constexpr float kRescaleThreshold = 8.0f;   // log2 units
 // every kPolyPeriod groups of four elements, one of the two pairs is a polynomial (1 of 2 -> 25 %).  0 disables.
 // Measured on B200 (profiles/README.md): 25 % helps head dim 64 (+4..8 %) and the dropout kernels (+3 %), and costs
 // 2 % on the D=128 no-dropout kernel, which therefore keeps every exponential on the MUFU.
+#ifndef FASN_POLY_PERIOD_D64
+#define FASN_POLY_PERIOD_D64 2
+#endif
 constexpr int kPolyPeriod = 2;
 
 
@@ -69,6 +72,11 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // D=128: P is handed to the tensor pipe in two halves (measured +6 % at S=8192); at D=64 the MMAs are too short
   // for the extra barrier round to pay (-3 %), so P is handed over whole.
   constexpr bool kSplitPV = (D == 128);
+  // D=64: tensor memory has room for P_t in columns of its own ([384,512)), so S_t is free as soon as the softmax threads
+  // have READ it and Q.K^T of the next K/V tile is issued during the softmax of the current one, instead of after its
+  // P.V -- at D=64 the MMAs are short and the serial chain Q.K^T -> softmax -> P.V per tile was the limiter.
+  // (At D=128 the 512 columns are full: S0 S1 O0 O1.)
+  constexpr bool kSepP = (D == 64);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -199,7 +207,8 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           const int k = half * 4 + kb;
-          umma_ts(tm + 256 + t * D, tm + t * 128 + k * 8, umma_desc_join(b0 + k * (2048 >> 4), hi_desc), idesc_pv, (half > 0 || kb > 0) ? 1u : acc);
+          umma_ts(tm + 256 + t * D, tm + (kSepP ? 384 + t * 64 : t * 128) + k * 8, umma_desc_join(b0 + k * (2048 >> 4), hi_desc), idesc_pv,
+                  (half > 0 || kb > 0) ? 1u : acc);
         }
       };
       TLF_DECL(0)
@@ -223,6 +232,20 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const bool more = (j + 1 < n_tiles);
         mbar_wait(&v_full[s], ph);
         if (more) mbar_wait(&k_full[s1], ph1);
+        if (kSepP && more) {
+          // Q.K^T of the next K/V tile as soon as the softmax threads have read S_t (p_full2 = "S_t has been read")
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (j + 1 < (t == 0 ? n_tiles0 : n_tiles1)) {
+              mbar_wait(&p_full2[t], j & 1);
+              tc_fence_after();
+              if (elect_one()) { issue_qk(t, s1); tc_commit(&s_full[t]); }
+              __syncwarp();
+            }
+          }
+          if (elect_one()) tc_commit(&k_empty[s1]);
+          __syncwarp();
+        }
         if (j < n_tiles0) {
           mbar_wait(&p_full[0], j & 1);
           tc_fence_after();
@@ -237,7 +260,7 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             if (!kSplitPV) issue_pv_half(0, s, 0, j > 0 ? 1u : 0u);
             issue_pv_half(0, s, 1, 1u);
             tc_commit(&o_full[0]);
-            if (j + 1 < n_tiles0) { issue_qk(0, s1); tc_commit(&s_full[0]); }
+            if (!kSepP && j + 1 < n_tiles0) { issue_qk(0, s1); tc_commit(&s_full[0]); }
           }
           __syncwarp();
         }
@@ -255,13 +278,13 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             if (!kSplitPV) issue_pv_half(1, s, 0, j > 0 ? 1u : 0u);
             issue_pv_half(1, s, 1, 1u);
             tc_commit(&o_full[1]);
-            if (j + 1 < n_tiles1) { issue_qk(1, s1); tc_commit(&s_full[1]); }
+            if (!kSepP && j + 1 < n_tiles1) { issue_qk(1, s1); tc_commit(&s_full[1]); }
           }
           __syncwarp();
         }
         if (elect_one()) {
           tc_commit(&v_empty[s]);
-          if (more) tc_commit(&k_empty[s1]);
+          if (!kSepP && more) tc_commit(&k_empty[s1]);
         }
         __syncwarp();
         TLF(4);
@@ -346,6 +369,7 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         TLF(11);
         tmem_wait_ld();
         TLF(12);
+        if (kSepP) { tc_fence_before(); mbar_arrive(&p_full2[t]); }      // S_t may be overwritten by the next Q.K^T
       }
       if constexpr (GENERIC) {
 #pragma unroll
@@ -481,7 +505,7 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const float2 a01 = __ffma2_rn(make_float2(s[c], s[c + 1]), cmul2, negm2);
             const float2 a23 = __ffma2_rn(make_float2(s[c + 2], s[c + 3]), cmul2, negm2);
             float p0 = ex2(a01.x), p1 = ex2(a01.y), p2, p3;
-            if (((c >> 2) % kPolyPeriod) < kPolyCount) { const float2 e = exp2_poly_pair(a23); p2 = e.x; p3 = e.y; }
+            if (((c >> 2) % (D == 64 ? FASN_POLY_PERIOD_D64 : kPolyPeriod)) < kPolyCount) { const float2 e = exp2_poly_pair(a23); p2 = e.x; p3 = e.y; }
             else { p2 = ex2(a23.x); p3 = ex2(a23.y); }
             finish4(c, p0, p1, p2, p3);
           }
@@ -493,8 +517,10 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             finish4(c, ex2(a01.x), ex2(a01.y), ex2(a23.x), ex2(a23.y));
           }
         }
-        // P columns [32 hf, 32 hf + 32) <- keys [64 hf, 64 hf + 64): over S columns this thread has already read
-        tmem_st_x32(tS + hf * 32, pr + hf * 32);
+        // P columns [32 hf, 32 hf + 32) <- keys [64 hf, 64 hf + 64): over S columns this thread has already read (D=128),
+        // or in P_t's own columns once the previous P.V has consumed them (D=64)
+        if (kSepP && hf == 0 && j > 0) { mbar_wait(&o_full[t], (j - 1) & 1); tc_fence_after(); }
+        tmem_st_x32((kSepP ? tmem_base + lane_off + 384 + t * 64 : tS) + hf * 32, pr + hf * 32);
         if (kSplitPV || hf == 1) {
           tmem_wait_st();
           tc_fence_before();
