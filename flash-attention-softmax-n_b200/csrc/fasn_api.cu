@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -109,7 +110,10 @@ int check_common(const FasnParams* p) {
   if (p->head_dim != 64 && p->head_dim != 128) return fail(FASN_EUNSUPPORTED, "head_dim %d: only 64 and 128", p->head_dim);
   if (p->batch <= 0 || p->heads <= 0 || p->seqlen_q <= 0 || p->seqlen_kv <= 0) return fail(FASN_EINVAL, "batch/heads/seqlen must be positive");
   if (p->heads_kv != p->heads && p->heads_kv != 1) return fail(FASN_EINVAL, "heads_kv must equal heads or 1");
-  if ((long long)p->batch * p->heads > 65535) return fail(FASN_EUNSUPPORTED, "batch*heads > 65535 per call: shard the batch x head axis");
+  {  // one-dimensional grids: (batch*heads) x tiles CTAs per launch
+    const long long tiles = ((long long)(p->seqlen_q > p->seqlen_kv ? p->seqlen_q : p->seqlen_kv) + 127) / 128 + 1;
+    if ((long long)p->batch * p->heads * tiles > 0x7FFFFFFFll) return fail(FASN_EUNSUPPORTED, "batch*heads*tiles exceeds 2^31-1 CTAs per launch: shard the batch x head axis");
+  }
   if (!(p->softmax_n >= 0.f)) return fail(FASN_EINVAL, "softmax_n must be >= 0");
   if (!(p->dropout_p >= 0.f && p->dropout_p < 1.f)) return fail(FASN_EINVAL, "dropout_p must be in [0,1)");
   if (!std::isfinite(p->scale)) return fail(FASN_EINVAL, "scale must be finite");
@@ -343,6 +347,45 @@ int fasn_dropout_mask(uint8_t* out, int32_t batch, int32_t heads, int32_t seqlen
   cudaError_t e = fasn::launch_dropout_mask(out, batch, heads, seqlen_q, seqlen_kv, keep_threshold(dropout_p),
                                             fasn::make_philox_key(philox_seed, philox_offset, keep_threshold(dropout_p)), (uint32_t)bh_offset, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda(e, "fasn_dropout_mask launch");
+  return 0;
+}
+
+namespace {
+bool sm_pair_ok(uint32_t in, uint32_t out) { return in <= 2 && out <= 2 && (in == out || in == 2 || out == 2); }
+int sm_vec(int cols, std::initializer_list<const void*> ptrs, std::initializer_list<long long> strides) {
+  if (cols % 8) return 0;
+  for (const void* q : ptrs) if (reinterpret_cast<uintptr_t>(q) & 15) return 0;
+  for (long long st : strides) if (st % 8) return 0;
+  return 1;
+}
+}  // namespace
+
+int fasn_softmax_n_fwd(const void* x, void* y, int64_t rows, int32_t cols, int64_t x_row_stride, int64_t y_row_stride,
+                       uint32_t dtype_in, uint32_t dtype_out, float n, void* stream) {
+  if (x == nullptr || y == nullptr || rows < 0 || cols <= 0) return fail(FASN_EINVAL, "fasn_softmax_n_fwd: bad argument");
+  if (!sm_pair_ok(dtype_in, dtype_out)) return fail(FASN_EUNSUPPORTED, "fasn_softmax_n_fwd: unsupported dtype pair (%u -> %u)", dtype_in, dtype_out);
+  if (!(n >= 0.f)) return fail(FASN_EINVAL, "softmax_n must be >= 0");
+  if (rows > 0x7FFFFFFFll) return fail(FASN_EUNSUPPORTED, "fasn_softmax_n_fwd: more than 2^31-1 rows per call");
+  if (rows == 0) return 0;
+  DeviceGuard guard(x);
+  if (guard.err != cudaSuccess) return fail_cuda(guard.err, "x is not a device pointer / cannot bind its device");
+  cudaError_t e = fasn::launch_softmax_n_fwd(x, y, rows, cols, x_row_stride, y_row_stride, (int)dtype_in, (int)dtype_out, n,
+                                             sm_vec(cols, {x, y}, {x_row_stride, y_row_stride}), (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(e, "fasn_softmax_n_fwd launch");
+  return 0;
+}
+
+int fasn_softmax_n_bwd(const void* y, const void* dy, void* dx, int64_t rows, int32_t cols, int64_t y_row_stride,
+                       int64_t dy_row_stride, int64_t dx_row_stride, uint32_t dtype_in, uint32_t dtype_out, void* stream) {
+  if (y == nullptr || dy == nullptr || dx == nullptr || rows < 0 || cols <= 0) return fail(FASN_EINVAL, "fasn_softmax_n_bwd: bad argument");
+  if (!sm_pair_ok(dtype_in, dtype_out)) return fail(FASN_EUNSUPPORTED, "fasn_softmax_n_bwd: unsupported dtype pair (%u -> %u)", dtype_in, dtype_out);
+  if (rows > 0x7FFFFFFFll) return fail(FASN_EUNSUPPORTED, "fasn_softmax_n_bwd: more than 2^31-1 rows per call");
+  if (rows == 0) return 0;
+  DeviceGuard guard(y);
+  if (guard.err != cudaSuccess) return fail_cuda(guard.err, "y is not a device pointer / cannot bind its device");
+  cudaError_t e = fasn::launch_softmax_n_bwd(y, dy, dx, rows, cols, y_row_stride, dy_row_stride, dx_row_stride, (int)dtype_in, (int)dtype_out,
+                                             sm_vec(cols, {y, dy, dx}, {y_row_stride, dy_row_stride, dx_row_stride}), (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(e, "fasn_softmax_n_bwd launch");
   return 0;
 }
 

@@ -102,6 +102,11 @@ cudaError_t launch_bwd2(bool bf16, bool causal, bool dropout, const CUtensorMap&
                         cudaStream_t stream);
 cudaError_t launch_bwd_finish(int head_dim, bool bf16, const TensorView& dq, const BwdArgs& a, cudaStream_t stream);
 
+// standalone softmax_n over the last axis (fasn_softmax.cu); dtype codes 0 fp16, 1 bf16, 2 fp32
+cudaError_t launch_softmax_n_fwd(const void* x, void* y, long long rows, int cols, long long sx, long long sy, int dt_in, int dt_out,
+                                 float n, int vec, cudaStream_t st);
+cudaError_t launch_softmax_n_bwd(const void* y, const void* dy, void* dx, long long rows, int cols, long long sy, long long sdy,
+                                 long long sdx, int dt_in, int dt_out, int vec, cudaStream_t st);
 cudaError_t launch_dropout_mask(uint8_t* out, int B, int H, int Sq, int Skv, uint32_t thr, PhiloxKey key,
                                 uint32_t bh_offset, cudaStream_t stream);
 cudaError_t launch_probe_pair(int mode, bool bf16, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& ty64,

@@ -136,6 +136,19 @@ int fasn_dropout_mask(uint8_t* out, int32_t batch, int32_t heads, int32_t seqlen
  *   mode 12: C[256x128] = X[256x128] * Y[128x128]     (M = 256, A in tensor memory) */
 int fasn_probe(int mode, uint32_t dtype, const void* x, const void* y, float* c, void* stream);
 
+/* Standalone fused softmax_n over the last (contiguous) axis: y_i = exp(x_i) / (n + sum_j exp(x_j)) for `rows` rows of
+ * `cols` elements, row strides in elements.  Replaces the eager `softmax_n`
+ * (flash_attention_softmax_n/core/functional.py:15-29: four elementwise passes) where a model cannot use the fused
+ * attention (the reference's surgery: surgery_functions/_bert.py:101, _xlnet.py:62).  dtype codes: FASN_FP16,
+ * FASN_BF16, FASN_FP32; (in, out) pairs: equal types, 16-bit -> fp32, fp32 -> 16-bit.  A row without any finite entry
+ * gives 0 (the reference gives NaN for n = 0).  Backward: dx_i = y_i (dy_i - sum_j y_j dy_j); y and dy in the forward's
+ * output dtype, dx in its input dtype. */
+#define FASN_FP32 2u
+int fasn_softmax_n_fwd(const void* x, void* y, int64_t rows, int32_t cols, int64_t x_row_stride, int64_t y_row_stride,
+                       uint32_t dtype_in, uint32_t dtype_out, float n, void* stream);
+int fasn_softmax_n_bwd(const void* y, const void* dy, void* dx, int64_t rows, int32_t cols, int64_t y_row_stride,
+                       int64_t dy_row_stride, int64_t dx_row_stride, uint32_t dtype_in, uint32_t dtype_out, void* stream);
+
 /* Host-buffer convenience used for end-to-end measurement: copies q,k,v (and dout) from HOST memory,
  * runs fwd (+bwd when dout_host != NULL) and copies o (and dq,dk,dv) back.  Contiguous (B,H,S,D) layouts.
  * Uses an internal device arena sized on first use; synchronises `stream` before returning. */
