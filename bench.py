@@ -52,6 +52,8 @@ WORKLOADS = {
                   desc="configs[2] shape, no dropout, dense key-padding attn_mask (B,1,1,S) AND causal (diagnostic)"),
     "c3alibi": dict(B=2, H=16, S=4096, D=128, dtype="f16", n=0.5, causal=True, dropout=0.0, bwd=True, aux="alibi",
                     desc="B=2 H=16 S=4096 D=128 with a dense ALiBi attn_bias (H,L,S) (diagnostic; 512 MiB of bias per pass)"),
+    "c3alibis": dict(B=2, H=16, S=4096, D=128, dtype="f16", n=0.5, causal=True, dropout=0.0, bwd=True, aux="alibi_slopes",
+                     desc="as c3alibi, but the ALiBi bias is generated in the kernels from 16 slopes (_alibi_slopes) (diagnostic)"),
     "c2": dict(B=8, H=16, S=2048, D=64, dtype="bf16", n=1.0, causal=False, dropout=0.0, bwd=False,
                desc="BASELINE.json configs[1]: fwd bf16 B=8 H=16 S=2048 D=64 n=1 non-causal"),
     "c4": dict(B=8, H=40, S=8192, D=128, dtype="bf16", n=1.0, causal=True, dropout=0.0, bwd=False,
@@ -233,6 +235,8 @@ def run_ours(args, w):
         slopes = 2.0 ** (-8.0 * torch.arange(1, H + 1, device=dev) / H)
         dist_ = (torch.arange(S, device=dev)[None, :] - torch.arange(S, device=dev)[:, None]).float()
         kw["attn_bias"] = (slopes[:, None, None] * dist_[None]).to(dtype)
+    elif w.get("aux") == "alibi_slopes":
+        kw["_alibi_slopes"] = 2.0 ** (-8.0 * torch.arange(1, H + 1, device=dev) / H)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if args.flush_l2 else None
 
     def step(i):

@@ -118,6 +118,7 @@ int check_common(const FasnParams* p) {
   if (!(p->dropout_p >= 0.f && p->dropout_p < 1.f)) return fail(FASN_EINVAL, "dropout_p must be in [0,1)");
   if (!std::isfinite(p->scale)) return fail(FASN_EINVAL, "scale must be finite");
   if (p->lse == nullptr) return fail(FASN_EINVAL, "lse is null");
+  if (p->alibi_slopes != nullptr && p->bias.ptr != nullptr) return fail(FASN_EINVAL, "alibi_slopes and bias are mutually exclusive");
   return 0;
 }
 
@@ -209,6 +210,7 @@ int fasn_fwd(const FasnParams* p) {
   a.o = tensor_view(p->o);
   a.mask = aux_view(p->mask);
   a.bias = aux_view(p->bias);
+  a.alibi = p->alibi_slopes;
   a.drop_thr = keep_threshold(p->dropout_p);
   a.inv_keep = 1.0f / (1.0f - p->dropout_p);
   a.key = fasn::make_philox_key(p->philox_seed, p->philox_offset, a.drop_thr);
@@ -270,6 +272,7 @@ int fasn_bwd(const FasnParams* p) {
   a.Sqp = (L + 127) / 128 * 128;
   a.mask = aux_view(p->mask);
   a.bias = aux_view(p->bias);
+  a.alibi = p->alibi_slopes;
   a.drop_thr = keep_threshold(p->dropout_p);
   a.inv_keep = 1.0f / (1.0f - p->dropout_p);
   a.key = fasn::make_philox_key(p->philox_seed, p->philox_offset, a.drop_thr);
@@ -287,7 +290,8 @@ int fasn_bwd(const FasnParams* p) {
   // Main kernel: the CTA-pair kernel (fasn_bwd2.cu) for head dim 128 without dense mask / bias, else the single-CTA
   // kernel.  FASN_BWD_IMPL=1 in the environment forces the single-CTA kernel (A/B measurements, parity tests of both).
   const int impl = g_bwd_impl.load();
-  const bool paired = (impl == 2 || (impl == 0 && FASN_BWD_AUTO_PAIRED)) && D == 128 && p->mask.ptr == nullptr && p->bias.ptr == nullptr;
+  const bool paired = (impl == 2 || (impl == 0 && FASN_BWD_AUTO_PAIRED)) && D == 128 && p->mask.ptr == nullptr && p->bias.ptr == nullptr &&
+                      p->alibi_slopes == nullptr;
   CUtensorMap tq64, tdo64, tdq64;
   if (paired) {
     if (int rc = make_map(&tq64, p->q.ptr, p->q.stride_b, p->q.stride_h, p->q.stride_s, B, H, L, D, bf16, "q", 64)) return rc;

@@ -353,7 +353,8 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const bool key_masked = key_only_mask && (*mbase == 0);
     if (key_only_mask) mbase = nullptr;
     const bool kv_valid = (kv_row < a.Skv) && !key_masked;
-    const bool has_aux = AUX && ((mbase != nullptr) || (a.bias.ptr != nullptr));
+    const bool has_aux = AUX && ((mbase != nullptr) || (a.bias.ptr != nullptr) || (a.alibi != nullptr));
+    const float alibi2 = (AUX && a.alibi != nullptr) ? a.alibi[h] * kLog2e : 0.f;
     const uint16_t* bbase = a.bias.ptr ? reinterpret_cast<const uint16_t*>(a.bias.ptr) + b * a.bias.sb + h * a.bias.sh + kv_c : nullptr;
     const uint32_t bh_global = a.bh_offset + bh;
     const uint32_t kvw = (uint32_t)(kv_row >> 5);          // identical for the 32 lanes of this warp
@@ -426,7 +427,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 64; c += 2) {
           const float2 l2 = *reinterpret_cast<const float2*>(lse_s + c);
-          float b0 = 0.f, b1 = 0.f;
+          float b0 = alibi2 * (float)(kv_row - a.causal_off - qc0 - c) * kLn2, b1 = b0 - alibi2 * kLn2;   // ALiBi (natural-log units here)
           if (bbase) { b0 = cvt16_to_f32<BF16>((uint16_t)(bpk[AUX ? (c >> 1) : 0] & 0xFFFF)); b1 = cvt16_to_f32<BF16>((uint16_t)(bpk[AUX ? (c >> 1) : 0] >> 16)); }
           const float x0 = fmaf(p[c], a.scale_log2, b0 * kLog2e) - l2.x;
           const float x1 = fmaf(p[c + 1], a.scale_log2, b1 * kLog2e) - l2.y;
@@ -581,7 +582,7 @@ template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
 static cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
                                 const CUtensorMap& tdk, const CUtensorMap& tdv, const CUtensorMap& tdq, const BwdArgs& a, const TensorView& dk,
                                 const TensorView& dv, cudaStream_t stream) {
-  const bool aux = a.bias.ptr != nullptr || (a.mask.ptr != nullptr && a.mask.sq != 0);
+  const bool aux = a.bias.ptr != nullptr || a.alibi != nullptr || (a.mask.ptr != nullptr && a.mask.sq != 0);
   return aux ? launch_bwd_t2<D, BF16, CAUSAL, DROPOUT, true>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv, stream)
              : launch_bwd_t2<D, BF16, CAUSAL, DROPOUT, false>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv, stream);
 }

@@ -28,6 +28,7 @@ struct FwdArgs {
   float* lse;             // (B,H,Sq)
   TensorView o;           // only used by the "no visible keys" early-out
   AuxView mask, bias;
+  const float* alibi;     // H slopes or null: logit(i, j) += alibi[h] * (j - i - causal_off)   (generic kernels)
   uint32_t drop_thr;      // keep iff u8 < drop_thr
   float inv_keep;         // 1/(1-p)
   PhiloxKey key;
@@ -47,6 +48,7 @@ struct BwdArgs {
   float* dq_accum;        // (B,H,Sqp,D) fp32
   int Sqp;                // Sq rounded up to 128
   AuxView mask, bias;
+  const float* alibi;     // H slopes or null (generic kernels)
   uint32_t drop_thr;
   float inv_keep;         // 1/(1-p)
   float keep_prob;        // 1-p

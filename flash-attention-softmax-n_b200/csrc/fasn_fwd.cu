@@ -322,6 +322,7 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float cmul = generic ? 1.f : a.scale_log2;
     const float2 cmul2 = make_float2(cmul, cmul);
 
+    const float alibi2 = (GENERIC && a.alibi != nullptr) ? a.alibi[h] * kLog2e : 0.f;
     float m = (a.softmax_n > 0.f) ? 0.f : -INFINITY;   // running reference max (log2 domain)
     float l = a.softmax_n;                             // running sum, starts at n (the virtual zero-logit key)
 
@@ -372,8 +373,14 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (kSepP) { tc_fence_before(); mbar_arrive(&p_full2[t]); }      // S_t may be overwritten by the next Q.K^T
       }
       if constexpr (GENERIC) {
+        if (a.alibi != nullptr) {       // ALiBi generated in place: + slope (j - i - (S - L)), log2 domain
+          const float base = alibi2 * (float)(j0 - row - a.causal_off);
 #pragma unroll
-        for (int c = 0; c < 128; ++c) s[c] *= a.scale_log2;
+          for (int c = 0; c < 128; ++c) s[c] = fmaf(s[c], a.scale_log2, fmaf(alibi2, (float)c, base));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) s[c] *= a.scale_log2;
+        }
         if (has_aux) {
           // dense bias / mask rows of this thread: 16-byte loads where the row segment is aligned and in range
           // (each thread streams its own 256 B / 128 B per tile; lines are shared by consecutive instructions via L1)
@@ -597,7 +604,7 @@ static cudaError_t launch_fwd_t2(const CUtensorMap& tq, const CUtensorMap& tk, c
 template <int D, bool BF16, bool CAUSAL, bool DROPOUT>
 static cudaError_t launch_fwd_t(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to,
                                 const FwdArgs& a, cudaStream_t stream) {
-  const bool generic = a.bias.ptr != nullptr || (a.mask.ptr != nullptr && a.mask.sq != 0) || !(a.scale_log2 > 0.f);
+  const bool generic = a.bias.ptr != nullptr || a.alibi != nullptr || (a.mask.ptr != nullptr && a.mask.sq != 0) || !(a.scale_log2 > 0.f);
   return generic ? launch_fwd_t2<D, BF16, CAUSAL, DROPOUT, true>(tq, tk, tv, to, a, stream)
                  : launch_fwd_t2<D, BF16, CAUSAL, DROPOUT, false>(tq, tk, tv, to, a, stream);
 }

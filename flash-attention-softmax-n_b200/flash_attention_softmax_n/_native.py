@@ -45,6 +45,7 @@ class FasnParams(ctypes.Structure):
         ("philox_seed", ctypes.c_uint64), ("philox_offset", ctypes.c_uint64), ("bh_offset", ctypes.c_int64),
         ("mask", FasnAux), ("bias", FasnAux),
         ("stream", ctypes.c_void_p),
+        ("alibi_slopes", ctypes.c_void_p),
     ]
 
 

@@ -78,7 +78,7 @@ def _prepare_aux(attn_mask: Optional[Tensor], attn_bias: Optional[Tensor], q: Te
 
 def _fill_common(p: _native.FasnParams, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, heads_kv: int,
                  n: float, scale: float, causal: bool, dropout_p: float, seed: int, offset: int, bh_offset: int,
-                 mask: Optional[Tensor], bias: Optional[Tensor]) -> None:
+                 mask: Optional[Tensor], bias: Optional[Tensor], alibi: Optional[Tensor] = None) -> None:
     B, H, L, D = q.shape
     p.struct_size = ctypes.sizeof(_native.FasnParams)
     p.dtype = _native.dtype_code(q.dtype)
@@ -89,6 +89,7 @@ def _fill_common(p: _native.FasnParams, q: Tensor, k: Tensor, v: Tensor, o: Tens
     p.softmax_n, p.scale, p.is_causal, p.dropout_p = float(n), float(scale), int(bool(causal)), float(dropout_p)
     p.philox_seed, p.philox_offset, p.bh_offset = seed, offset, bh_offset
     p.mask, p.bias = _native.aux_view(mask), _native.aux_view(bias)
+    p.alibi_slopes = alibi.data_ptr() if alibi is not None else None
     p.stream = _native.current_stream_ptr(q.device)
 
 
@@ -99,22 +100,22 @@ class _FusedAttentionN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q: Tensor, k: Tensor, v: Tensor, heads_kv: int, n: float, scale: float, causal: bool,
                 dropout_p: float, mask: Optional[Tensor], bias: Optional[Tensor], seed: int, offset: int,
-                bh_offset: int) -> Tensor:
+                bh_offset: int, alibi: Optional[Tensor] = None) -> Tensor:
         lib = _native.load()
         B, H, L, D = q.shape
         with torch.cuda.device(q.device):
             o = torch.empty((B, H, L, D), dtype=q.dtype, device=q.device)     # fresh outputs (flash_attn_triton.py:271)
             lse = torch.empty((B, H, L), dtype=torch.float32, device=q.device)
             p = _native.FasnParams()
-            _fill_common(p, q, k, v, o, lse, heads_kv, n, scale, causal, dropout_p, seed, offset, bh_offset, mask, bias)
+            _fill_common(p, q, k, v, o, lse, heads_kv, n, scale, causal, dropout_p, seed, offset, bh_offset, mask, bias, alibi)
             _native.check(lib.fasn_fwd(ctypes.byref(p)), "fasn_fwd")
-        ctx.save_for_backward(q, k, v, o, lse, mask, bias)
+        ctx.save_for_backward(q, k, v, o, lse, mask, bias, alibi)
         ctx.cfg = (heads_kv, n, scale, causal, dropout_p, seed, offset, bh_offset)
         return o
 
     @staticmethod
     def backward(ctx, do: Tensor):
-        q, k, v, o, lse, mask, bias = ctx.saved_tensors
+        q, k, v, o, lse, mask, bias, alibi = ctx.saved_tensors
         heads_kv, n, scale, causal, dropout_p, seed, offset, bh_offset = ctx.cfg
         lib = _native.load()
         B, H, L, D = q.shape
@@ -129,14 +130,14 @@ class _FusedAttentionN(torch.autograd.Function):
             ws = torch.empty((2, B, H, Lp), dtype=torch.float32, device=q.device)
             dq_accum = torch.empty((B, H, Lp, D), dtype=torch.float32, device=q.device)
             p = _native.FasnParams()
-            _fill_common(p, q, k, v, o, lse, heads_kv, n, scale, causal, dropout_p, seed, offset, bh_offset, mask, bias)
+            _fill_common(p, q, k, v, o, lse, heads_kv, n, scale, causal, dropout_p, seed, offset, bh_offset, mask, bias, alibi)
             p.dout, p.dq, p.dk, p.dv = (_native.tensor_view(t) for t in (do, dq, dk, dv))
             p.delta, p.dq_accum = ws.data_ptr(), dq_accum.data_ptr()
             _native.check(lib.fasn_bwd(ctypes.byref(p)), "fasn_bwd")
         if heads_kv == 1 and H > 1:
             dk = dk.sum(dim=1, keepdim=True, dtype=torch.float32).to(q.dtype)
             dv = dv.sum(dim=1, keepdim=True, dtype=torch.float32).to(q.dtype)
-        return dq, dk, dv, None, None, None, None, None, None, None, None, None, None
+        return dq, dk, dv, None, None, None, None, None, None, None, None, None, None, None
 
 
 def flash_attention_n(
@@ -152,6 +153,7 @@ def flash_attention_n(
         *,
         _philox: Optional[Tuple[int, int]] = None,
         _bh_offset: int = 0,
+        _alibi_slopes: Optional[Tensor] = None,
 ) -> Tensor:
     """
     Fused attention with softmax_n on B200.
@@ -169,6 +171,8 @@ def flash_attention_n(
 
     `_philox` (seed, offset) pins the dropout stream and `_bh_offset` is the global index of the first
     (batch, head) unit of this call; both exist for tests and for batch x head sharding (parallel.py).
+    `_alibi_slopes` (H,) generates the ALiBi bias  slopes[h] * (j - i - (S - L))  inside the kernels, equivalent to (and
+    exclusive with) passing that (H, L, S) tensor as `attn_bias`, without its B*H*L*S elements of HBM traffic.
     """
     n = 0.0 if softmax_n_param is None else float(softmax_n_param)
     if n < 0:
@@ -205,8 +209,15 @@ def flash_attention_n(
 
     query, key, value = _rowmajor(query), _rowmajor(key), _rowmajor(value)
     mask, bias = _prepare_aux(attn_mask, attn_bias, query, S)
+    alibi = None
+    if _alibi_slopes is not None:
+        if bias is not None:
+            raise ValueError("_alibi_slopes and attn_bias are mutually exclusive")
+        if _alibi_slopes.shape != (H,):
+            raise ValueError(f"_alibi_slopes must have shape ({H},), got {tuple(_alibi_slopes.shape)}")
+        alibi = _alibi_slopes.detach().to(device=query.device, dtype=torch.float32).contiguous()
     seed, offset = (0, 0)
     if dropout_p > 0.0:
         seed, offset = _philox if _philox is not None else _next_philox(query.device)
     return _FusedAttentionN.apply(query, key, value, heads_kv, n, sm_scale, bool(is_causal), float(dropout_p),
-                                  mask, bias, int(seed), int(offset), int(_bh_offset))
+                                  mask, bias, int(seed), int(offset), int(_bh_offset), alibi)

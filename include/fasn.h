@@ -89,6 +89,11 @@ typedef struct FasnParams {
   FasnAux  bias;          /* same dtype as q; added after scaling (flash_attn.py:81-83,100-113)         */
 
   void*    stream;        /* cudaStream_t                                                               */
+
+  /* ALiBi generated in the kernels instead of a dense (H,L,S) attn_bias tensor:
+   * NULL, or H fp32 slopes on the device; the logit of (i, j) gets  + alibi_slopes[h] * (j - i - (S - L)),
+   * i.e. slope times the signed distance to the bottom-right aligned diagonal.  Exclusive with `bias`. */
+  const float* alibi_slopes;
 } FasnParams;
 
 /* ABI version of the loaded library (== FASN_ABI_VERSION it was built with). */

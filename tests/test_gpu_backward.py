@@ -190,3 +190,21 @@ def test_backward_key_padding_mask(fasn_lib, D, causal, with_bias):
     for bi, n in enumerate(lens.tolist()):
         assert float(got[2][bi, :, n:].abs().max() if n < S else 0.0) == 0.0
         assert float(got[3][bi, :, n:].abs().max() if n < S else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,H,L,S,D,causal", [(2, 4, 256, 256, 128, True), (1, 3, 200, 333, 64, False), (1, 2, 333, 200, 128, True)])
+def test_alibi_slopes_equal_the_dense_bias(fasn_lib, B, H, L, S, D, causal, dtype):
+    """`_alibi_slopes` generates slopes[h] * (j - i - (S - L)) in the kernels: same results as the dense (H, L, S) attn_bias
+    (flash_attn.py:62 names ALiBi as the use of attn_bias) in forward and backward."""
+    q, k, v, do = make_qkv(B, H, L, S, D, dtype, seed=31)
+    slopes = 2.0 ** (-8.0 * torch.arange(1, H + 1) / H)
+    dist = (torch.arange(S)[None, :] - torch.arange(L)[:, None] - (S - L)).double()
+    bias = slopes.double()[:, None, None] * dist[None]
+    kw = dict(softmax_n_param=1.0, is_causal=causal)
+    got = run_fused(q, k, v, do, _alibi_slopes=slopes.cuda(), **kw)
+    want = oracle_all(q, k, v, do, attn_bias=bias, **kw)
+    for name, a, b in zip(("O", "dQ", "dK", "dV"), got, want):
+        check_close(name + "(alibi)", a, b, None, dtype, rel_scale=1.5)
+    with pytest.raises(ValueError):
+        run_fused(q, k, v, do, _alibi_slopes=slopes.cuda(), attn_bias=bias.to(dtype).cuda(), **kw)
