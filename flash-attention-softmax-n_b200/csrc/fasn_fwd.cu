@@ -501,7 +501,10 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         pr[c >> 1] = w01;
         pr[(c >> 1) + 1] = w23;
       };
-      constexpr int kPolyCount = (D == 64 || DROPOUT) ? 1 : 0;
+#ifndef FASN_POLY_DROPOUT
+#define FASN_POLY_DROPOUT 1
+#endif
+      constexpr int kPolyCount = (D == 64 || (DROPOUT && FASN_POLY_DROPOUT)) ? 1 : 0;
       const bool use_poly = kPolyCount > 0 && !generic && !masked_tile;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
