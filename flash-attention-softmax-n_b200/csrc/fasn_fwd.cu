@@ -20,7 +20,12 @@
 // The running max is only moved when it grows by more than 2^8 (lazy rescale), so the O accumulator in TMEM is
 // rescaled rarely; exponent arguments stay <= 8 and P fits fp16/bf16.
 //
-// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D);  P_t aliases the first 64 columns of S_t.
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D);  P_t aliases the first 64 columns of S_t at
+// D=128 and has columns of its own ([384,512)) at D=64 (kSepP below).
+//
+// Launch: one-dimensional grid, work order decode_block (fasn_common.cuh): unit-major with a tile-major tail, heavy
+// causal blocks first.  GENERIC instantiations carry the dense attn_mask / attn_bias / ALiBi code; a key-padding mask
+// (row stride 0) is handled on the fast path.
 #include "fasn_common.cuh"
 #include "fasn_ptx.cuh"
 
