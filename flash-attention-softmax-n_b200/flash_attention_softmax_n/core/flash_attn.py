@@ -160,7 +160,7 @@ def flash_attention_n(
 
     :param query: Query tensor; shape (N, H, L, E).
     :param key: Key tensor; shape (N, H, S, E) or (N, S, E) (shared by all heads).
-    :param value: Value tensor; shape (N, H, S, Ev) or (N, S, Ev); Ev == E.
+    :param value: Value tensor; shape (N, H, S, Ev) or (N, S, Ev).  E, Ev <= 128 (64 and 128 run unpadded).
     :param softmax_n_param: Regularization parameter n >= 0 of softmax_n (any real number; None = 0).
     :param scale: Scaling factor applied prior to softmax. If None, the default value is set to 1 / sqrt(E).
     :param dropout_p: Dropout probability; if greater than 0.0, dropout is applied.
@@ -200,13 +200,23 @@ def flash_attention_n(
     S = key.shape[2]
     if key.shape[0] != B or value.shape[0] != B or value.shape[2] != S or key.shape[3] != E:
         raise ValueError("inconsistent query/key/value shapes")
-    if value.shape[3] != E or E not in _SUPPORTED_HEAD_DIMS:
-        raise NotImplementedError(f"fused kernel supports E == Ev in {_SUPPORTED_HEAD_DIMS}, got E={E}, "
-                                  f"Ev={value.shape[3]}; use slow_attention_n")
+    Ev = value.shape[3]
+    if max(E, Ev) > max(_SUPPORTED_HEAD_DIMS):
+        raise NotImplementedError(f"fused kernel supports head dims up to {max(_SUPPORTED_HEAD_DIMS)}, got E={E}, Ev={Ev}; "
+                                  "use slow_attention_n")
+    # The kernels are built for E == Ev in {64, 128}.  Other head dims (the Triton path's 16 / 32, flash_attn_triton.py:266;
+    # Ev != E on the SDPA path, README.md:50) are zero-padded up to the next supported size: zero feature columns change
+    # neither Q K^T nor the first Ev output columns, and autograd carries the gradients through the pad / slice.
+    Dp = min(d for d in _SUPPORTED_HEAD_DIMS if d >= max(E, Ev))
     if not 0.0 <= dropout_p < 1.0:
         raise ValueError("dropout_p must be in [0, 1)")
     sm_scale = 1.0 / sqrt(E) if scale is None else float(scale)           # flash_attn.py:59, 81-83
 
+    if E != Dp:
+        query = torch.nn.functional.pad(query, (0, Dp - E))
+        key = torch.nn.functional.pad(key, (0, Dp - E))
+    if Ev != Dp:
+        value = torch.nn.functional.pad(value, (0, Dp - Ev))
     query, key, value = _rowmajor(query), _rowmajor(key), _rowmajor(value)
     mask, bias = _prepare_aux(attn_mask, attn_bias, query, S)
     alibi = None
@@ -219,5 +229,6 @@ def flash_attention_n(
     seed, offset = (0, 0)
     if dropout_p > 0.0:
         seed, offset = _philox if _philox is not None else _next_philox(query.device)
-    return _FusedAttentionN.apply(query, key, value, heads_kv, n, sm_scale, bool(is_causal), float(dropout_p),
-                                  mask, bias, int(seed), int(offset), int(_bh_offset), alibi)
+    out = _FusedAttentionN.apply(query, key, value, heads_kv, n, sm_scale, bool(is_causal), float(dropout_p),
+                                 mask, bias, int(seed), int(offset), int(_bh_offset), alibi)
+    return out if Ev == Dp else out[..., :Ev]

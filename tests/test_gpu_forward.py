@@ -139,7 +139,28 @@ def test_forward_strided_inputs_and_errors(fasn_lib):
     with pytest.raises(NotImplementedError):
         flash_attention_n(q.float(), k.float(), v.float())
     with pytest.raises(NotImplementedError):
-        flash_attention_n(q[..., :32], k[..., :32], v[..., :32])
+        big = torch.zeros(1, 1, 8, 160, dtype=dtype, device="cuda")
+        flash_attention_n(big, big, big)                                         # head dims above 128
+
+
+@pytest.mark.parametrize("E,Ev", [(32, 32), (16, 16), (64, 128), (128, 64), (80, 48), (8, 8)])
+def test_other_head_dims_are_zero_padded(fasn_lib, E, Ev):
+    """Head dims other than 64 / 128 (the Triton path's 16 / 32, flash_attn_triton.py:266) and Ev != E (README.md:50) run
+    zero-padded to the next supported size; results and gradients equal the oracle's on the unpadded tensors."""
+    from tests._util import run_fused, oracle_all
+    dtype = torch.bfloat16
+    B, H, L, S = 2, 2, 150, 210
+    g = torch.Generator().manual_seed(E * 131 + Ev)
+    q = (torch.randn(B, H, L, E, generator=g) * 0.5).to(dtype).cuda()
+    k = (torch.randn(B, H, S, E, generator=g) * 0.5).to(dtype).cuda()
+    v = (torch.randn(B, H, S, Ev, generator=g) * 0.5).to(dtype).cuda()
+    do = torch.randn(B, H, L, Ev, generator=g).to(dtype).cuda()
+    kw = dict(softmax_n_param=1.0, is_causal=True)
+    got = run_fused(q, k, v, do, **kw)
+    want = oracle_all(q, k, v, do, **kw)
+    for name, a, b in zip(("O", "dQ", "dK", "dV"), got, want):
+        assert a.shape == b.shape, (name, a.shape, b.shape)
+        check_close(f"{name}(E={E},Ev={Ev})", a, b, None, dtype, rel_scale=1.5)
 
 
 @pytest.mark.parametrize("scale", [-0.2, 0.0])
