@@ -92,23 +92,93 @@ def local_attention(q_units: Tensor, k_units: Tensor, v_units: Tensor, unit_offs
 
 def sharded_attention(query: Optional[Tensor], key: Optional[Tensor], value: Optional[Tensor], *,
                       shape: Tuple[int, int, int, int, int], dtype: torch.dtype, device: torch.device,
-                      root: int = 0, group=None, attn_fn: Optional[Callable] = None, **kwargs) -> Optional[Tensor]:
+                      root: int = 0, group=None, attn_fn: Optional[Callable] = None, chunks: int = 1,
+                      **kwargs) -> Optional[Tensor]:
     """Scatter (B,H,L,D)/(B,H,S,D) tensors held by `root` over the group by (batch, head) slabs, run attention
     on every rank, gather O on the root.  `shape` = (B, H, L, S, D) must be passed on every rank.
-    Returns (B,H,L,D) on the root and None elsewhere.  attn_mask / attn_bias are not sharded here."""
+    Returns (B,H,L,D) on the root and None elsewhere.  attn_mask / attn_bias are not sharded here.
+
+    `chunks` > 1 cuts every rank's slab into that many pieces and software-pipelines them: while the kernels work on
+    piece c, piece c+1 is in flight from the root and the output of piece c-1 is in flight back (one batched
+    point-to-point group per step, NCCL on its own stream), so a step costs about max(transfer, kernels) instead of
+    their sum.  The root's own slab is never copied."""
     if "attn_mask" in kwargs or "attn_bias" in kwargs:
         raise NotImplementedError("sharded_attention does not distribute attn_mask / attn_bias")
     B, H, L, S, D = shape
     n_units = B * H
-    rank = dist.get_rank(group)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
     on_root = rank == root
-    qf = query.reshape(n_units, L, D).contiguous() if on_root else None
-    kf = key.reshape(n_units, S, D).contiguous() if on_root else None
-    vf = value.reshape(n_units, S, D).contiguous() if on_root else None
-    ql = scatter_units(qf, (L, D), dtype, device, n_units, root, group)
-    kl = scatter_units(kf, (S, D), dtype, device, n_units, root, group)
-    vl = scatter_units(vf, (S, D), dtype, device, n_units, root, group)
-    lo, _ = partition_units(n_units, dist.get_world_size(group))[rank]
-    ol = local_attention(ql, kl, vl, lo, attn_fn=attn_fn, **kwargs)
-    full = gather_units(ol.contiguous(), n_units, root, group)
-    return full.reshape(B, H, L, D) if on_root else None
+    qf = query.reshape(n_units, L, D) if on_root else None
+    kf = key.reshape(n_units, S, D) if on_root else None
+    vf = value.reshape(n_units, S, D) if on_root else None
+    if on_root:
+        qf, kf, vf = qf.contiguous(), kf.contiguous(), vf.contiguous()
+    if chunks <= 1:
+        ql = scatter_units(qf, (L, D), dtype, device, n_units, root, group)
+        kl = scatter_units(kf, (S, D), dtype, device, n_units, root, group)
+        vl = scatter_units(vf, (S, D), dtype, device, n_units, root, group)
+        lo, _ = partition_units(n_units, world)[rank]
+        ol = local_attention(ql, kl, vl, lo, attn_fn=attn_fn, **kwargs)
+        full = gather_units(ol.contiguous(), n_units, root, group)
+        return full.reshape(B, H, L, D) if on_root else None
+
+    peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    parts = partition_units(n_units, world)
+    # piece c of rank r: global units [parts[r][0] + sub[r][c][0], parts[r][0] + sub[r][c][1])
+    sub = [partition_units(b - a, chunks) for a, b in parts]
+    piece = lambda r, c: (parts[r][0] + sub[r][c][0], parts[r][0] + sub[r][c][1])
+    out_full = torch.empty((n_units, L, D), dtype=dtype, device=device) if on_root else None
+    inbuf: List[Optional[Tuple[Tensor, Tensor, Tensor]]] = [None] * chunks
+    outbuf: List[Optional[Tensor]] = [None] * chunks
+    reqs_in: List[list] = [[] for _ in range(chunks)]
+    reqs_out: list = []
+    waited = set()
+
+    for step in range(chunks + 2):
+        ops = []
+        c_in, c_out = step, step - 2
+        if c_in < chunks:                                   # scatter piece c_in
+            if on_root:
+                for r in range(world):
+                    a, b = piece(r, c_in)
+                    if r != root and b > a:
+                        ops += [dist.P2POp(dist.isend, t[a:b], peer(r), group) for t in (qf, kf, vf)]
+                a, b = piece(root, c_in)
+                inbuf[c_in] = (qf[a:b], kf[a:b], vf[a:b])     # views: the root's own slab is not copied
+            else:
+                a, b = piece(rank, c_in)
+                bufs = tuple(torch.empty((b - a, n, D), dtype=dtype, device=device) for n in (L, S, S))
+                inbuf[c_in] = bufs
+                if b > a:
+                    ops += [dist.P2POp(dist.irecv, t, peer(root), group) for t in bufs]
+        if 0 <= c_out < chunks:                             # gather the output of piece c_out
+            if on_root:
+                for r in range(world):
+                    a, b = piece(r, c_out)
+                    if r != root and b > a:
+                        ops.append(dist.P2POp(dist.irecv, out_full[a:b], peer(r), group))
+            else:
+                a, b = piece(rank, c_out)
+                if b > a:
+                    ops.append(dist.P2POp(dist.isend, outbuf[c_out], peer(root), group))
+        posted = dist.batch_isend_irecv(ops) if ops else []
+        if c_in < chunks:
+            reqs_in[c_in] = posted                          # (a group completes as a whole: its gather ops ride along)
+        reqs_out += posted
+        c = step - 1                                        # compute piece c while the group above is in flight
+        if 0 <= c < chunks:
+            for w in reqs_in[c]:
+                w.wait()
+                waited.add(id(w))
+            a, b = piece(rank, c)
+            qc, kc, vc = inbuf[c]
+            oc = local_attention(qc, kc, vc, a, attn_fn=attn_fn, **kwargs).contiguous()
+            if on_root:
+                out_full[a:b].copy_(oc)
+            else:
+                outbuf[c] = oc
+            inbuf[c] = None
+    for w in reqs_out:
+        if id(w) not in waited:       # (a second wait() on a completed gloo work blocks)
+            w.wait()
+    return out_full.reshape(B, H, L, D) if on_root else None

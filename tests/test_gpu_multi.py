@@ -30,9 +30,11 @@ def _worker(rank, world, port, ret):
         kw = dict(softmax_n_param=0.5, is_causal=True, dropout_p=0.1, _philox=(17, 4))
         out = sharded_attention(q if rank == 0 else None, k if rank == 0 else None, v if rank == 0 else None,
                                 shape=(B, H, L, S, D), dtype=torch.bfloat16, device=dev, **kw)
+        out3 = sharded_attention(q if rank == 0 else None, k if rank == 0 else None, v if rank == 0 else None,
+                                 shape=(B, H, L, S, D), dtype=torch.bfloat16, device=dev, chunks=3, **kw)   # pipelined pieces
         if rank == 0:
             ref = flash_attention_n(q, k, v, **kw)
-            ret["equal"] = bool(torch.equal(out, ref))
+            ret["equal"] = bool(torch.equal(out, ref)) and bool(torch.equal(out3, ref))
     finally:
         dist.destroy_process_group()
 

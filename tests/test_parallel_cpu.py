@@ -53,6 +53,9 @@ def _worker(rank, world, port, B, H, L, S, D, ret):
         out = sharded_attention(q if rank == 0 else None, k if rank == 0 else None, v if rank == 0 else None,
                                 shape=(B, H, L, S, D), dtype=torch.float64, device=torch.device("cpu"),
                                 attn_fn=slow_attention_n, **kw)
+        out3 = sharded_attention(q if rank == 0 else None, k if rank == 0 else None, v if rank == 0 else None,
+                                 shape=(B, H, L, S, D), dtype=torch.float64, device=torch.device("cpu"),
+                                 attn_fn=slow_attention_n, chunks=3, **kw)      # software-pipelined pieces
         # scatter followed by gather is the identity
         flat = q.reshape(B * H, L, D).contiguous()
         loc = scatter_units(flat if rank == 0 else None, (L, D), torch.float64, torch.device("cpu"), B * H)
@@ -61,8 +64,9 @@ def _worker(rank, world, port, B, H, L, S, D, ret):
             ref = slow_attention_n(q, k, v, **kw)
             ret["err"] = (out - ref).abs().max().item()
             ret["roundtrip"] = bool(torch.equal(back, flat))
+            ret["err_chunked"] = (out3 - ref).abs().max().item()
         else:
-            assert out is None and back is None
+            assert out is None and back is None and out3 is None
     finally:
         dist.destroy_process_group()
 
@@ -74,3 +78,4 @@ def test_sharded_attention_world2_gloo(B, H):
     mp.spawn(_worker, args=(2, _free_port(), B, H, 12, 20, 8, ret), nprocs=2, join=True)
     assert ret["roundtrip"] is True
     assert ret["err"] < 1e-12
+    assert ret["err_chunked"] < 1e-12
