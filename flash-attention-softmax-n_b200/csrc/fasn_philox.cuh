@@ -5,7 +5,8 @@
 // regenerate the same mask in whatever thread layout they like, and results do not depend on how the
 // batch x head axis is sharded over GPUs.
 //
-// One 32-bit "keep word" covers keys 32*w .. 32*w+31 of one query row.  Two Philox-4x32-10 calls give eight
+// One 32-bit "keep word" covers keys 32*w .. 32*w+31 of one query row.  Two Philox-4x32-7 calls (FASN_PHILOX_ROUNDS: the
+// variant FlashAttention-2 uses and the smallest Crush-resistant one of Salmon et al., SC'11) give eight
 // 32-bit planes; plane p carries bit (7-p) of 32 independent 8-bit uniforms (bit-sliced), and u < T is
 // evaluated with a bitwise comparator (MSB first) -- 16 keep decisions per Philox call, ~0.5 ALU op per
 // decision for the compare.  P(keep) = T/256 with T = round(256 (1-p)).
@@ -13,7 +14,7 @@
 #include <cstdint>
 
 #ifndef FASN_PHILOX_ROUNDS
-#define FASN_PHILOX_ROUNDS 10
+#define FASN_PHILOX_ROUNDS 7
 #endif
 
 namespace fasn {

@@ -134,3 +134,22 @@ def test_dropout_mask_properties():
     assert torch.equal(tail.reshape(2, 64, 200), m.reshape(6, 64, 200)[4:])
     assert not torch.equal(m, orc.dropout_keep_mask(0x5EED, 4, 2, 3, 64, 200, p))
     assert orc.dropout_keep_mask(1, 0, 1, 1, 8, 40, 0.0).all()
+
+
+def test_dropout_generator_statistics():
+    """The kernels' generator (Philox-4x32-7 planes + bitwise threshold compare): keep rate T/256 and no visible correlation
+    between neighbouring keys, neighbouring rows, neighbouring units or the two Philox calls of a word."""
+    B, H, L, S, p = 2, 2, 256, 1024, 0.1
+    keep = orc.dropout_keep_mask(0x5EED, 3, B, H, L, S, p).numpy().astype(np.float64)
+    T = orc.keep_threshold(p)
+    rate, n = keep.mean(), keep.size
+    assert abs(rate - T / 256.0) < 5 * np.sqrt(rate * (1 - rate) / n)
+    z = keep - rate
+    var = z.var()
+    for a, b in [(z[..., :-1], z[..., 1:]), (z[..., :-1, :], z[..., 1:, :]), (z[:, :-1], z[:, 1:]), (z[..., :-32], z[..., 32:]),
+                 (z[..., :-16], z[..., 16:])]:
+        corr = (a * b).mean() / var
+        assert abs(corr) < 6.0 / np.sqrt(a.size), corr
+    # different (seed, offset) streams are unrelated
+    other = orc.dropout_keep_mask(0x5EED, 4, B, H, L, S, p).numpy().astype(np.float64) - rate
+    assert abs((z * other).mean() / var) < 6.0 / np.sqrt(n)
