@@ -1,0 +1,95 @@
+"""Host logic of the Hugging Face route (`flash_attention_softmax_n.surgery`): registration,
+the eager softmax_n route against the library's own eager attention, mask decomposition.  No kernels run here."""
+import pytest
+import torch
+
+transformers = pytest.importorskip("transformers")
+from transformers import BertConfig, BertModel, LlamaConfig, LlamaModel  # noqa: E402
+
+from flash_attention_softmax_n.surgery import EAGER, FUSED, apply_attention_softmax_n  # noqa: E402
+from flash_attention_softmax_n.surgery import attention_softmax_n as S  # noqa: E402
+
+
+def _bert():
+    torch.manual_seed(0)
+    return BertModel(BertConfig(hidden_size=128, num_attention_heads=2, num_hidden_layers=2, intermediate_size=256,
+                                vocab_size=100, max_position_embeddings=64), add_pooling_layer=False).eval()
+
+
+def _llama():
+    torch.manual_seed(0)
+    return LlamaModel(LlamaConfig(hidden_size=128, num_attention_heads=4, num_key_value_heads=2, num_hidden_layers=2,
+                                  intermediate_size=256, vocab_size=100)).eval()
+
+
+def _inputs():
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(0, 100, (2, 16), generator=g)
+    am = torch.ones(2, 16, dtype=torch.long)
+    am[1, 10:] = 0
+    return ids, am
+
+
+@pytest.mark.parametrize("make", [_bert, _llama])
+def test_eager_route_with_n0_is_the_models_own_attention(make):
+    model = make()
+    ids, am = _inputs()
+    model.config._attn_implementation = "eager"
+    with torch.no_grad():
+        want = model(input_ids=ids, attention_mask=am).last_hidden_state
+        count = apply_attention_softmax_n(model, 0.0, implementation=EAGER)
+        assert count == 2 and model.config._attn_implementation == EAGER
+        got = model(input_ids=ids, attention_mask=am).last_hidden_state
+        valid = am.bool()
+        assert torch.allclose(got[valid], want[valid], atol=5e-6)
+        apply_attention_softmax_n(model, 1.0, implementation=EAGER)
+        other = model(input_ids=ids, attention_mask=am).last_hidden_state
+        assert (other[valid] - want[valid]).abs().max() > 1e-3          # n changes the result
+
+
+def test_n_is_stamped_on_every_attention_module_and_validated():
+    model = _bert()
+    assert apply_attention_softmax_n(model, 0.5) == 2                  # default: the fused route
+    assert model.config._attn_implementation == FUSED
+    stamped = [m.softmax_n_param for m in model.modules() if hasattr(m, "softmax_n_param")]
+    assert stamped == [0.5, 0.5]
+    with pytest.raises(ValueError):
+        apply_attention_softmax_n(model, -1.0)
+    with pytest.raises(ValueError):
+        apply_attention_softmax_n(model, 1.0, implementation="sdpa")
+    assert apply_attention_softmax_n(torch.nn.Linear(4, 4), 1.0) == 0   # nothing to switch: warns, returns 0
+
+
+def test_fused_route_has_no_cpu_fallback():
+    model = _bert()
+    apply_attention_softmax_n(model, 1.0)
+    ids, am = _inputs()
+    with pytest.raises((NotImplementedError, RuntimeError, ValueError, AssertionError, TypeError)):
+        model(input_ids=ids, attention_mask=am)
+
+
+def test_unstamped_module_is_an_error():
+    S.register_attention_softmax_n()
+    model = _bert()
+    model.config._attn_implementation = EAGER
+    ids, am = _inputs()
+    with pytest.raises(RuntimeError, match="apply_attention_softmax_n"):
+        model(input_ids=ids, attention_mask=am)
+
+
+def test_mask_decomposition():
+    B, L, Sk = 2, 8, 12
+    keypad = torch.ones(B, 1, 1, Sk, dtype=torch.bool)
+    keypad[1, ..., 9:] = False
+    dense = keypad.expand(B, 1, L, Sk).contiguous()
+    m, causal = S._decompose_mask(dense, L, Sk)
+    assert m.shape == (B, 1, 1, Sk) and not causal and torch.equal(m, keypad)
+    tri = torch.arange(Sk).view(1, Sk) <= torch.arange(L).view(L, 1) + (Sk - L)
+    m, causal = S._decompose_mask((keypad & tri).contiguous(), L, Sk)
+    assert causal and torch.equal(m & tri, keypad & tri)
+    odd = dense.clone()
+    odd[0, 0, 3, 2] = False                                              # neither pattern: stays dense
+    m, causal = S._decompose_mask(odd, L, Sk)
+    assert m is odd and not causal
+    again, _ = S._decompose_mask(odd, L, Sk)                             # cached
+    assert again is odd
