@@ -41,6 +41,10 @@ namespace {
 #define TL(tag)
 #endif
 
+#ifndef FASN_DQ_DIRECT
+#define FASN_DQ_DIRECT 0
+#endif
+
 constexpr int kBwdThreads = 512;
 
 template <int D> struct BwdCfg {
@@ -305,6 +309,35 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     constexpr int NCH = D / 32;                           // 32-column chunks per dQ tile
     TL_DECL(3)
     TL_ONLY(threadIdx.x == 256);
+#if FASN_DQ_DIRECT
+    // Direct variant: tcgen05.ld shape 16x256b puts 32 contiguous bytes of a dQ row into each quad of lanes, so one
+    // red.global.add.v2.f32 per thread adds whole 32-byte sectors at the L2 -- no shared-memory staging (the staged TMA
+    // reduce costs 128 KB of shared-memory traffic per Q tile in a kernel that is bound by that port).
+    const int g = lane >> 2, t2 = (lane & 3) * 2;
+    for (int it = 0; it < n_iter; ++it) {
+      const int qi0 = (i_start + it) * 128;
+      float* dst = a.dq_accum + ((long long)bh * a.Sqp + qi0 + (warp & 3) * 32 + g) * D + t2;
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+      TL(30);
+#pragma unroll
+      for (int hb = 0; hb < D / 64; ++hb) {
+        uint32_t v[64];
+        tmem_ld_16x256b_x8(tmem_base + lane_off + TM_DQ + hb * 64, v);
+        tmem_ld_16x256b_x8(tmem_base + lane_off + (16u << 16) + TM_DQ + hb * 64, v + 32);
+        tmem_wait_ld();
+        if (hb == D / 64 - 1) { tc_fence_before(); mbar_arrive(dq_empty); TL(31); }
+#pragma unroll
+        for (int h16 = 0; h16 < 2; ++h16)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float* p0 = dst + (h16 * 16) * D + hb * 64 + c * 8;
+            red_add_v2(p0, __uint_as_float(v[h16 * 32 + 4 * c]), __uint_as_float(v[h16 * 32 + 4 * c + 1]));
+            red_add_v2(p0 + 8 * D, __uint_as_float(v[h16 * 32 + 4 * c + 2]), __uint_as_float(v[h16 * 32 + 4 * c + 3]));
+          }
+      }
+    }
+#else
     for (int it = 0; it < n_iter; ++it) {
       const int qi0 = (i_start + it) * 128;
       mbar_wait(dq_full, it & 1);
@@ -336,6 +369,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #endif
       }
     }
+#endif
     if (threadIdx.x == 256) tma_store_wait_all();
   } else {
     // -------------------------------------------------------------------- compute warps
@@ -441,7 +475,11 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const float4 l4 = *reinterpret_cast<const float4*>(lse_s + c);
           const float2 a01 = __ffma2_rn(make_float2(p[c], p[c + 1]), c2, make_float2(-l4.x, -l4.y));
           const float2 a23 = __ffma2_rn(make_float2(p[c + 2], p[c + 3]), c2, make_float2(-l4.z, -l4.w));
+#ifdef FASN_EXP_NO_EX2      // diagnostic build only (wrong results): how much of the step the MUFU exponentials cost
+          p[c] = a01.x; p[c + 1] = a01.y; p[c + 2] = a23.x; p[c + 3] = a23.y;
+#else
           p[c] = ex2(a01.x); p[c + 1] = ex2(a01.y); p[c + 2] = ex2(a23.x); p[c + 3] = ex2(a23.y);
+#endif
         }
       }
       const bool diag = CAUSAL && (qi0 + a.causal_off < k0 + 127);     // some (q, kv) of this tile pair lies above the diagonal

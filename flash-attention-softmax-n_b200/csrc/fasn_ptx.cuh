@@ -224,6 +224,21 @@ FASN_DEVICE void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+// shape 16x256b.x8: 16 TMEM lanes x 64 columns.  Thread t holds, for column chunk c = 0..7 (8 columns each):
+//   r[4c], r[4c+1] = lane (base + t/4),     columns 8c + 2(t%4), +1
+//   r[4c+2], r[4c+3] = lane (base + t/4 + 8), the same columns
+// i.e. the four threads of a quad hold 32 contiguous bytes of one row (one L2 sector).
+FASN_DEVICE void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+FASN_DEVICE void red_add_v2(float* gptr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};\n" ::"l"(gptr), "f"(a), "f"(b) : "memory");
+}
 FASN_DEVICE void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
