@@ -69,6 +69,14 @@ def algorithmic_flops(w):
     return f, (2.5 * f if w["bwd"] else 0.0)
 
 
+def algorithmic_bytes(w):
+    """HBM bytes a step must move: forward reads Q, K, V and writes O (+ fp32 LSE); the backward
+    reads Q, K, V, O, dO (+ LSE, delta) and writes dQ, dK, dV."""
+    rows, es = w["B"] * w["H"] * w["S"], 2
+    fwd = 4 * rows * w["D"] * es + 4 * rows
+    return fwd, ((8 * rows * w["D"] * es + 8 * rows) if w["bwd"] else 0)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -338,6 +346,12 @@ def run_ours(args, w):
                 "peak_kind": "sustained bf16 dense, " + peaks["source"], "frac_of_burst_peak": achieved / peaks["burst"],
                 "fwd_kernel_ms": fwd_ms.value / max(fwd_n.value, 1),
                 "fwd_kernel_tflops": f_fwd / (fwd_ms.value / max(fwd_n.value, 1) * 1e-3) / 1e12 if fwd_n.value else None}
+    # secondary: the step's algorithmic HBM traffic rate (every workload here is far above the 248 FLOP/B ridge, C5 included)
+    b_fwd, b_bwd = algorithmic_bytes(w)
+    roofline["hbm_algorithmic_bytes_per_step"] = b_fwd + b_bwd
+    roofline["hbm_algorithmic_gbps"] = (b_fwd + b_bwd) * args.steps / (ms_max * 1e-3) / 1e9      # per GPU
+    roofline["hbm_frac_of_copy_peak"] = roofline["hbm_algorithmic_gbps"] / peaks["hbm"]
+    roofline["flop_per_byte"] = flops_step / (b_fwd + b_bwd)
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
