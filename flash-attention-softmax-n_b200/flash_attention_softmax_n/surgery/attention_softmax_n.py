@@ -16,6 +16,13 @@ needed: two attention functions are registered with that interface,
 both fed boolean masks (True = attend) by the library's `sdpa_mask` builder, and `apply_attention_softmax_n` stamps n on
 every attention module of the model and switches its config to one of them.  Keeps the reference's signature
 (`model, softmax_n_param, optimizers`); nothing is re-allocated, so `optimizers` has nothing to update.
+
+Attention cores that cannot be expressed as fused attention -- XLNet's relative-position scores are a sum of three
+query-dependent terms (`XLNetRelativeAttention.rel_attn_core`, the reference's surgery_functions/_xlnet.py:25-75) -- keep
+their own score arithmetic and get the softmax inside them replaced: their core method runs under a torch-function mode
+that turns `torch.nn.functional.softmax` / `Tensor.softmax` into the fused row kernel `softmax_n_fused` (one read and one
+write per score, forward and backward; fp16 / bf16 / fp32 on CUDA) or, for ``"softmax_n_eager"``, the eager `softmax_n`.
+No forward copies: the library's own method body is what runs.
 """
 from __future__ import annotations
 
@@ -27,8 +34,11 @@ import torch
 from torch import Tensor
 from torch.nn import Module
 
+from torch.overrides import TorchFunctionMode
+
 from flash_attention_softmax_n.core.flash_attn import flash_attention_n
-from flash_attention_softmax_n.core.functional import slow_attention_n
+from flash_attention_softmax_n.core.functional import slow_attention_n, softmax_n
+from flash_attention_softmax_n.core.softmax import softmax_n_fused
 
 log = logging.getLogger(__name__)
 
@@ -133,6 +143,41 @@ def register_attention_softmax_n() -> None:
         ALL_MASK_ATTENTION_FUNCTIONS.register(name, sdpa_mask)
 
 
+# method name -> classes (by name) whose attention core keeps its own score arithmetic and only has its softmax replaced
+_SOFTMAX_CORES = {"XLNetRelativeAttention": "rel_attn_core"}
+_SOFTMAX_FUNCS = (torch.nn.functional.softmax, torch.softmax, Tensor.softmax)
+
+
+class _SoftmaxNMode(TorchFunctionMode):
+    """Inside the mode every softmax call is softmax_n with the given n (other functions pass through untouched)."""
+
+    def __init__(self, n: float, impl):
+        super().__init__()
+        self.n, self.impl = n, impl
+
+    def __torch_function__(self, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func in _SOFTMAX_FUNCS:
+            x = args[0] if args else kwargs["input"]
+            dim = args[1] if len(args) > 1 else kwargs.get("dim", -1)
+            dtype = kwargs.get("dtype", args[3] if len(args) > 3 and func is torch.nn.functional.softmax else None)
+            return self.impl(x, n=self.n, dim=dim, dtype=dtype)
+        return func(*args, **kwargs)
+
+
+def _wrap_softmax_core(module: Module, method: str, implementation: str) -> None:
+    """Instance-level patch: `module.<method>` runs the class's own method under `_SoftmaxNMode`."""
+    original = getattr(type(module), method)
+    impl = softmax_n_fused if implementation == FUSED else softmax_n
+
+    def core(*args, **kwargs):
+        with _SoftmaxNMode(getattr(module, _ATTR), impl):
+            return original(module, *args, **kwargs)
+
+    core.__wrapped__ = original
+    setattr(module, method, core)
+
+
 def _is_attention_module(m: Module) -> bool:
     cfg = getattr(m, "config", None)
     return cfg is not None and hasattr(cfg, "_attn_implementation") and (
@@ -157,12 +202,17 @@ def apply_attention_softmax_n(model: Module, softmax_n_param: float, optimizers=
     count = 0
     configs = {}
     for m in model.modules():
-        if _is_attention_module(m) and not isinstance(m, type(model)):
+        core = _SOFTMAX_CORES.get(type(m).__name__)
+        if core is not None and hasattr(m, core):
+            setattr(m, _ATTR, float(softmax_n_param))
+            _wrap_softmax_core(m, core, implementation)
+            count += 1
+        elif _is_attention_module(m) and not isinstance(m, type(model)):
             setattr(m, _ATTR, float(softmax_n_param))
             configs[id(m.config)] = m.config
             count += 1
     top = getattr(model, "config", None)
-    if top is not None and hasattr(top, "_attn_implementation"):
+    if configs and top is not None and hasattr(top, "_attn_implementation"):
         configs[id(top)] = top
     if count == 0:
         log.warning("AttentionSoftmaxN had no effect on the model: no module that dispatches through the transformers "

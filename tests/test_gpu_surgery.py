@@ -11,7 +11,7 @@ import pytest
 import torch
 
 transformers = pytest.importorskip("transformers")
-from transformers import BertConfig, BertModel, LlamaConfig, LlamaModel  # noqa: E402
+from transformers import BertConfig, BertModel, LlamaConfig, LlamaModel, XLNetConfig, XLNetModel  # noqa: E402
 
 from flash_attention_softmax_n.surgery import EAGER, FUSED, apply_attention_softmax_n  # noqa: E402
 from flash_attention_softmax_n.surgery import attention_softmax_n as S  # noqa: E402
@@ -87,3 +87,40 @@ def test_fused_route_matches_eager_softmax_n_route(make, n, padded):
         scale = want_g[name].abs().max().item()
         e, r = (got_g[name] - want_g[name]).abs().max().item(), (base_g[name] - want_g[name]).abs().max().item()
         assert e <= 2 * r + 2e-3 * scale, (name, e, r, scale)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_xlnet_core_on_the_fused_row_kernel(dtype):
+    """XLNet keeps its relative-position score arithmetic; its softmax runs on `softmax_n_fused`.  Against the eager
+    softmax_n route on the same weights: fp32 to 1e-4 (relative to the largest value), fp16 within 2 x the eager fp16 model's
+    own distance from the fp32 truth."""
+    torch.manual_seed(0)
+    truth = XLNetModel(XLNetConfig(d_model=256, n_head=4, n_layer=2, d_inner=512, vocab_size=1000, dropout=0.0)).cuda().train()
+    B, L = 3, 160
+    ids = torch.randint(0, 1000, (B, L), device="cuda")
+    am = torch.ones(B, L, device="cuda")
+    am[1, 100:] = 0
+    w = torch.randn(B, L, 256, device="cuda")
+    fused = copy.deepcopy(truth).to(dtype)
+    eager = copy.deepcopy(truth).to(dtype)
+    n = 1.0
+    apply_attention_softmax_n(truth, n, implementation=EAGER)
+    apply_attention_softmax_n(eager, n, implementation=EAGER)
+    assert apply_attention_softmax_n(fused, n) == 2
+
+    def run(model):
+        model.zero_grad(set_to_none=True)
+        out = model(input_ids=ids, attention_mask=am.to(next(model.parameters()).dtype)).last_hidden_state
+        (out.float() * w).sum().backward()
+        return out.detach().float(), model.layer[0].rel_attn.q.grad.detach().float()
+
+    got, got_g = run(fused)
+    want, want_g = run(truth)
+    base, base_g = run(eager)
+    assert torch.isfinite(got).all() and torch.isfinite(got_g).all()
+    for a, b, c in ((got, want, base), (got_g, want_g, base_g)):
+        scale = b.abs().max().item()
+        if dtype == torch.float32:
+            assert (a - b).abs().max().item() <= 1e-4 * scale + 1e-6
+        else:
+            assert (a - b).abs().max().item() <= 2 * (c - b).abs().max().item() + 2e-3 * scale

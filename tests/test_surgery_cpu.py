@@ -4,7 +4,7 @@ import pytest
 import torch
 
 transformers = pytest.importorskip("transformers")
-from transformers import BertConfig, BertModel, LlamaConfig, LlamaModel  # noqa: E402
+from transformers import BertConfig, BertModel, LlamaConfig, LlamaModel, XLNetConfig, XLNetModel  # noqa: E402
 
 from flash_attention_softmax_n.surgery import EAGER, FUSED, apply_attention_softmax_n  # noqa: E402
 from flash_attention_softmax_n.surgery import attention_softmax_n as S  # noqa: E402
@@ -93,3 +93,40 @@ def test_mask_decomposition():
     assert m is odd and not causal
     again, _ = S._decompose_mask(odd, L, Sk)                             # cached
     assert again is odd
+
+
+def test_xlnet_core_keeps_its_scores_and_gets_softmax_n():
+    """XLNet's relative-attention core (reference: surgery_functions/_xlnet.py:25-75) runs its own method body with the
+    softmax inside it replaced; n = 0 reproduces the unmodified model."""
+    torch.manual_seed(0)
+    model = XLNetModel(XLNetConfig(d_model=128, n_head=2, n_layer=2, d_inner=256, vocab_size=100)).eval()
+    ids, am = _inputs()
+    with torch.no_grad():
+        want = model(input_ids=ids, attention_mask=am.float()).last_hidden_state
+        assert apply_attention_softmax_n(model, 0.0, implementation=EAGER) == 2
+        got = model(input_ids=ids, attention_mask=am.float()).last_hidden_state
+        assert torch.allclose(got, want, atol=5e-6)
+        apply_attention_softmax_n(model, 1.0, implementation=EAGER)          # re-applying replaces, does not nest
+        other = model(input_ids=ids, attention_mask=am.float()).last_hidden_state
+        assert (other - want).abs().max() > 1e-3
+        # the eager definition, applied by hand to one layer's scores, is what the patched core computes
+        layer = model.layer[0].rel_attn
+        assert layer.softmax_n_param == 1.0 and layer.rel_attn_core.__wrapped__ is type(layer).rel_attn_core
+        apply_attention_softmax_n(model, 1.0)                                # fused route: CUDA only, no fallback
+        with pytest.raises(NotImplementedError):
+            model(input_ids=ids, attention_mask=am.float())
+
+
+def test_softmax_mode_maps_every_softmax_spelling():
+    from flash_attention_softmax_n import softmax_n
+    x = torch.randn(3, 5, 7)
+    with S._SoftmaxNMode(2.0, softmax_n):
+        a = torch.nn.functional.softmax(x, dim=1)
+        b = x.softmax(dim=-1)
+        c = torch.softmax(x, 2)
+        d = torch.nn.functional.softmax(x, dim=-1, dtype=torch.float64)
+        e = x.exp()                                                         # other functions pass through
+    assert torch.allclose(a, softmax_n(x, 2.0, dim=1)) and torch.allclose(b, softmax_n(x, 2.0, dim=-1))
+    assert torch.allclose(c, b) and d.dtype == torch.float64 and torch.allclose(d.float(), b, atol=1e-6)
+    assert torch.equal(e, torch.exp(x))
+    assert torch.allclose(torch.softmax(x, 2), torch.nn.functional.softmax(x, dim=2))     # and nothing leaks out of the mode
