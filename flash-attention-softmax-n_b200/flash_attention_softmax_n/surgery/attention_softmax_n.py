@@ -118,6 +118,11 @@ def attention_softmax_n_forward(module: Module, query: Tensor, key: Tensor, valu
     """`transformers` attention-interface function on the fused kernels.  query/key/value are (B, H, L|S, D);
     returns ((B, L, H, D) output, None): attention weights are never materialised."""
     n, key, value, mask, bias, causal = _common(module, query, key, value, attention_mask, is_causal, True)
+    if not query.is_cuda or query.dtype not in (torch.float16, torch.bfloat16):
+        raise NotImplementedError(
+            f"the '{FUSED}' route runs on CUDA tensors in float16 / bfloat16 (got {query.device.type}, {query.dtype}): move the "
+            f"model with .cuda().half() / .bfloat16() or run it under torch.autocast, or pass implementation='{EAGER}' to "
+            "apply_attention_softmax_n for the eager definition -- there is no silent fallback")
     out = flash_attention_n(query, key, value, softmax_n_param=n, scale=scaling, dropout_p=float(dropout),
                             attn_mask=mask, attn_bias=bias, is_causal=causal)
     return out.transpose(1, 2).contiguous(), None
