@@ -46,8 +46,13 @@ FUSED = "softmax_n_fused"
 EAGER = "softmax_n_eager"
 _ATTR = "softmax_n_param"
 
-__all__ = ["FUSED", "EAGER", "apply_attention_softmax_n", "attention_softmax_n_forward",
+__all__ = ["FUSED", "EAGER", "AttentionSoftmaxN", "apply_attention_softmax_n", "attention_softmax_n_forward",
            "eager_attention_softmax_n_forward", "register_attention_softmax_n"]
+
+try:                                             # MosaicML Composer is optional: only the trainer plug-in below needs it
+    from composer.core import Algorithm as _AlgorithmBase, Event as _Event
+except ImportError:                              # pragma: no cover - composer is not part of this image
+    _AlgorithmBase, _Event = object, None
 
 
 def _repeat_kv(x: Tensor, groups: int) -> Tensor:
@@ -228,3 +233,38 @@ def apply_attention_softmax_n(model: Module, softmax_n_param: float, optimizers=
         cfg._attn_implementation = implementation
     log.info("softmax_n attention (n = %s, %s) set on %d attention modules", softmax_n_param, implementation, count)
     return count
+
+
+class AttentionSoftmaxN(_AlgorithmBase):
+    """Composer trainer plug-in with the reference's name, constructor and behaviour (surgery/attention_softmax_n.py:66-108):
+    at `Event.INIT` it calls `apply_attention_softmax_n(state.model, softmax_n_param, optimizers=state.optimizers)` once.
+    `implementation` picks the fused (default) or the eager route.  Needs `mosaicml` (composer) to be used in a Trainer;
+    without it the object can still be constructed and `apply_to(model)` used directly."""
+
+    def __init__(self, softmax_n_param: float, implementation: str = FUSED) -> None:
+        self.softmax_n_param = softmax_n_param
+        self.implementation = implementation
+        self._applied = False
+
+    def __repr__(self) -> str:
+        return f"{self.__class__.__name__}()"
+
+    @staticmethod
+    def required_on_load() -> bool:
+        return True
+
+    def match(self, event, state) -> bool:
+        del state
+        if _Event is None:
+            raise RuntimeError("AttentionSoftmaxN.match needs MosaicML Composer (pip install mosaicml); "
+                               "call apply_to(model) or apply_attention_softmax_n(model, n) instead")
+        return event == _Event.INIT and not self._applied
+
+    def apply_to(self, model: Module, optimizers=None) -> int:
+        count = apply_attention_softmax_n(model, self.softmax_n_param, optimizers=optimizers, implementation=self.implementation)
+        self._applied = True
+        return count
+
+    def apply(self, event, state, logger) -> None:
+        del event, logger
+        self.apply_to(state.model, optimizers=state.optimizers)

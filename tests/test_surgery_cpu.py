@@ -130,3 +130,19 @@ def test_softmax_mode_maps_every_softmax_spelling():
     assert torch.allclose(c, b) and d.dtype == torch.float64 and torch.allclose(d.float(), b, atol=1e-6)
     assert torch.equal(e, torch.exp(x))
     assert torch.allclose(torch.softmax(x, 2), torch.nn.functional.softmax(x, dim=2))     # and nothing leaks out of the mode
+
+
+def test_trainer_plugin_keeps_the_reference_shape():
+    """`AttentionSoftmaxN(softmax_n_param)` (reference: surgery/attention_softmax_n.py:66-108): applies once, on the model it is
+    handed; the Composer event plumbing needs composer itself."""
+    from types import SimpleNamespace
+    from flash_attention_softmax_n.surgery import AttentionSoftmaxN
+    algo = AttentionSoftmaxN(softmax_n_param=1.0, implementation=EAGER)
+    assert repr(algo) == "AttentionSoftmaxN()" and AttentionSoftmaxN.required_on_load() and not algo._applied
+    model = _bert()
+    algo.apply(None, SimpleNamespace(model=model, optimizers=None), None)
+    assert algo._applied and model.config._attn_implementation == EAGER
+    assert [m.softmax_n_param for m in model.modules() if hasattr(m, "softmax_n_param")] == [1.0, 1.0]
+    if S._Event is None:
+        with pytest.raises(RuntimeError, match="Composer"):
+            algo.match(None, None)
