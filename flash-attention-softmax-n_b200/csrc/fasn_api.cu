@@ -394,7 +394,7 @@ int fasn_softmax_n_bwd(const void* y, const void* dy, void* dx, int64_t rows, in
 }
 
 int fasn_probe(int mode, uint32_t dtype, const void* x, const void* y, float* c, void* stream) {
-  if (!((mode >= 0 && mode <= 3) || (mode >= 10 && mode <= 12)) || x == nullptr || y == nullptr || c == nullptr) return fail(FASN_EINVAL, "bad argument");
+  if (!((mode >= 0 && mode <= 6) || (mode >= 10 && mode <= 12)) || x == nullptr || y == nullptr || c == nullptr) return fail(FASN_EINVAL, "bad argument");
   if (dtype != FASN_FP16 && dtype != FASN_BF16) return fail(FASN_EUNSUPPORTED, "dtype");
   const bool bf16 = dtype == FASN_BF16;
   DeviceGuard guard(x);

@@ -34,6 +34,8 @@ fasn_probe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   uint8_t* sY = smem + 2 * BLK;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sY + 2 * BLK);   // [0] tma, [1] mma done, [2] A staged in TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  uint8_t* sAx = sY + 2 * BLK + 1024;          // modes 4-6: extension operands (no-swizzle K-major, one K-step of 16)
+  uint8_t* sBx = sAx + 4096;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 4 && lane == 0) {
@@ -55,14 +57,14 @@ fasn_probe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         tma_load_4d(sY + db * BLK, &tm_y, &bars[0], db * 64, 0, 0, 0);
       }
       mbar_wait(&bars[0], 0);
-      if (mode == 1) mbar_wait(&bars[2], 0);
+      if (mode == 1 || mode >= 4) mbar_wait(&bars[2], 0);
       tc_fence_after();
       const uint32_t sX_u = smem_u32(sX), sY_u = smem_u32(sY);
       for (int kb = 0; kb < 8; ++kb) {
         const uint32_t koff = (kb >> 2) * BLK + (kb & 3) * 32;      // K-major advance
         const uint32_t moff = kb * 2048;                            // MN-major advance
         const uint32_t acc = kb > 0 ? 1u : 0u;
-        if (mode == 0)
+        if (mode == 0 || mode >= 4)
           umma_ss(tmem_base, umma_smem_desc(sX_u + koff, 16, 1024), umma_smem_desc(sY_u + koff, 16, 1024),
                   umma_idesc(BF16, 128, 128, false, false), acc);
         else if (mode == 1)
@@ -75,11 +77,44 @@ fasn_probe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           umma_ss(tmem_base, umma_smem_desc(sX_u + koff, 16, 1024), umma_smem_desc(sY_u + moff, BLK, 1024),
                   umma_idesc(BF16, 128, 128, false, true), acc);
       }
+      if (mode >= 4) {
+        // ninth K-step: C[i][j] += sum_k Ax[i][k] * Bx[j][k] with the extension operands written below.
+        //   mode 4: both 16-byte K-chunks and all sixteen 8-row groups stored (LBO = 128, SBO = 256)
+        //   mode 5: the second K-chunk aliases the first (LBO = 0, SBO = 128): the step counts every term twice
+        //   mode 6: mode 5 + the A side is ONE core matrix shared by all row groups (SBO = 0)
+        const uint32_t lbo = mode == 4 ? 128u : 0u, sbo = mode == 4 ? 256u : 128u;
+        umma_ss(tmem_base, umma_smem_desc_noswz(smem_u32(sAx), lbo, mode == 6 ? 0u : sbo), umma_smem_desc_noswz(smem_u32(sBx), lbo, sbo),
+                umma_idesc(BF16, 128, 128, false, false), 1u);
+      }
       tc_commit(&bars[1]);
     }
   } else {
     const int r = threadIdx.x;   // 0..127
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    if (mode >= 4) {
+      // A side: rows of (1, 1, 1, 0, ...); B side: row j = the three-term 16-bit split of e_j = 3.25 * x[j][0] (+ zeros).
+      // Expected: C = X Y^T + e_j (mode 4), + 2 e_j (modes 5, 6).
+      const uint16_t one = BF16 ? 0x3F80 : 0x3C00;
+      const float e = 3.25f * cvt16_to_f32<BF16>(x[r * 128]);
+      const uint16_t h0 = (uint16_t)(pack2<BF16>(e, 0.f) & 0xFFFF);
+      const float r1 = e - cvt16_to_f32<BF16>(h0);
+      const uint16_t h1 = (uint16_t)(pack2<BF16>(r1, 0.f) & 0xFFFF);
+      const uint16_t h2 = (uint16_t)(pack2<BF16>(r1 - cvt16_to_f32<BF16>(h1), 0.f) & 0xFFFF);
+      const uint4 arow = make_uint4(one | ((uint32_t)one << 16), one, 0u, 0u);
+      const uint4 brow = make_uint4(h0 | ((uint32_t)h1 << 16), h2, 0u, 0u);
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      if (mode == 4) {            // [row group][K-chunk][row in group][16 B]
+        *reinterpret_cast<uint4*>(sAx + (r >> 3) * 256 + (r & 7) * 16) = arow;
+        *reinterpret_cast<uint4*>(sAx + (r >> 3) * 256 + 128 + (r & 7) * 16) = zero;
+        *reinterpret_cast<uint4*>(sBx + (r >> 3) * 256 + (r & 7) * 16) = brow;
+        *reinterpret_cast<uint4*>(sBx + (r >> 3) * 256 + 128 + (r & 7) * 16) = zero;
+      } else {                    // [row group][row in group][16 B]; mode 6 reads only the first group of the A side
+        *reinterpret_cast<uint4*>(sAx + r * 16) = arow;
+        *reinterpret_cast<uint4*>(sBx + r * 16) = brow;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bars[2]);
+    }
     if (mode == 1) {
       uint32_t a[64];
       const uint32_t* src = reinterpret_cast<const uint32_t*>(x + r * 128);
@@ -259,7 +294,7 @@ cudaError_t launch_dropout_mask(uint8_t* out, int B, int H, int Sq, int Skv, uin
 
 cudaError_t launch_probe(int mode, bool bf16, const CUtensorMap& tx, const CUtensorMap& ty, const void* x, float* c,
                          cudaStream_t stream) {
-  constexpr int smem = 1024 + 4 * 128 * 128 + 64;
+  constexpr int smem = 1024 + 4 * 128 * 128 + 1024 + 2 * 4096;
   cudaError_t e;
   if (bf16) {
     e = cudaFuncSetAttribute(fasn_probe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

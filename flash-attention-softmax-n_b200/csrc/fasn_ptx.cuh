@@ -289,6 +289,18 @@ FASN_DEVICE uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint
   return d;
 }
 
+// No-swizzle ("interleaved") K-major operand: core matrix = 8 rows x 16 bytes stored contiguously (128 B); element
+// (row r, 16-byte K-chunk c) sits at  (r % 8) * 16 + (r / 8) * SBO + c * LBO.  Used by the bring-up probe for the one-K-step
+// "extension" operands of DESIGN.md section 8 (zero strides make chunks / row groups alias one another).
+FASN_DEVICE uint64_t umma_smem_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
 // Split form for issue loops: the high word is a constant per operand kind, the low word is
 // (start address >> 4) | (LBO >> 4) << 16, so stepping through a tile is one 32-bit add of (bytes >> 4).
 __host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }

@@ -134,6 +134,9 @@ int fasn_dropout_mask(uint8_t* out, int32_t batch, int32_t heads, int32_t seqlen
  *   mode 1: C = X * Y    (A from tensor memory, B MN-major)      -- the P V form
  *   mode 2: C = X^T * Y  (A, B MN-major in shared memory)        -- the dQ = dS K form
  *   mode 3: C = X * Y    (A K-major, B MN-major in shared memory)-- the dK = dS^T Q form
+ *   modes 4-6 (building block of the LSE2 fold): mode 0 plus a ninth K-step whose operands are no-swizzle K-major
+ *           "extension" tiles -- C = X * Y^T + e_j (4) or + 2 e_j (5: second K-chunk aliases the first, LBO = 0;
+ *           6: additionally one core matrix serves every row group of the A side, SBO = 0), e_j = 3.25 * x[j][0].
  * x, y: 128x128 row-major 16-bit device arrays; c: 128x128 row-major fp32.
  * CTA-pair forms (cluster of two CTAs, tcgen05 cta_group::2; the paired backward kernel):
  *   mode 10: C[256x128] = X[256x128] * Y[128x128]^T   (M = 256, B split along N between the two CTAs)
