@@ -44,6 +44,11 @@ namespace {
 #ifndef FASN_DQ_DIRECT
 #define FASN_DQ_DIRECT 0
 #endif
+// Experimental (not the default): fold -LSE2 into the S^T MMA as a ninth K-step instead of
+// delivering it to every compute thread through uniform-address shared-memory loads.
+#ifndef FASN_BWD_FOLD_LSE
+#define FASN_BWD_FOLD_LSE 0
+#endif
 
 constexpr int kBwdThreads = 512;
 
@@ -56,6 +61,9 @@ template <int D> struct BwdCfg {
   static constexpr int DQ_STAGE_BYTES = 128 * 32 * 4;             // dQ staging chunk: 128 rows x 32 fp32 columns
   // K, V, Q ring (2), dO (1), dS^T, dQ staging (2 chunks), LSE2 ring + delta ring (2 x 2 x 512 B), barriers, tmem slot
   static constexpr int SMEM_BYTES = 5 * TILE_BYTES + DS_BYTES + 2 * DQ_STAGE_BYTES + 4 * 512 + NUM_BARS * 8 + 16;
+  // FOLD: Q-tile extension (128 rows x 16 B), K-side extension (one 128-byte core matrix), delta (single buffer), barriers
+  static constexpr int QX_BYTES = 128 * 16, AX_BYTES = 128;
+  static constexpr int SMEM_BYTES_FOLD = 5 * TILE_BYTES + DS_BYTES + 2 * DQ_STAGE_BYTES + QX_BYTES + AX_BYTES + 512 + NUM_BARS * 8 + 16;
 };
 
 // TMA reduce-add shared -> global (fp32 tile added into the tensor at L2), bulk async-group completion
@@ -77,7 +85,7 @@ FASN_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, 
 
 // AUX = true: dense attn_mask / attn_bias tensors (generic path); AUX = false keeps that code out of the fast kernels
 // (a key-padding mask with row stride 0 is handled by both).
-template <int D, bool BF16, bool CAUSAL, bool DROPOUT, bool AUX>
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT, bool AUX, bool FOLD = false>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -85,6 +93,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const __grid_constant__ CUtensorMap tm_dq, const BwdArgs a,
                 const TensorView dk_view, const TensorView dv_view) {
   using Cfg = BwdCfg<D>;
+  static_assert(!(FOLD && AUX), "the LSE2 fold is built for the fast kernels only");
   constexpr int DB = Cfg::DB, TILE_BYTES = Cfg::TILE_BYTES, BLK_BYTES = Cfg::BLK_BYTES;
   constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 128, TM_DV = 256, TM_DK = 256 + D;
 
@@ -128,9 +137,12 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* sDO = sQ + 2 * TILE_BYTES;         // [1]
   uint8_t* sDS = sDO + TILE_BYTES;
   uint8_t* sDQ = sDS + Cfg::DS_BYTES;         // [2] fp32 staging chunks for the TMA reduce-add of dQ
+  // FOLD: [Q extension 2 KB][K-side extension 128 B][delta, single buffer 512 B] instead of the LSE2 and delta rings
+  uint8_t* sQx = sDQ + 2 * Cfg::DQ_STAGE_BYTES;
+  uint8_t* sAx = sQx + Cfg::QX_BYTES;
   float* sLse = reinterpret_cast<float*>(sDQ + 2 * Cfg::DQ_STAGE_BYTES);   // [2][128]
-  float* sDelta = sLse + 256;                                    // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
+  float* sDelta = FOLD ? reinterpret_cast<float*>(sAx + Cfg::AX_BYTES) : sLse + 256;   // [2][128] ([128] with FOLD)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + (FOLD ? 128 : 256));
   uint64_t* kv_full = bars + 0;
   uint64_t* q_full = bars + 1;     // [2]
   uint64_t* q_empty = bars + 3;    // [2]
@@ -145,6 +157,8 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* dq_empty = bars + 15;  // 128 arrivals
   uint64_t* dkv_full = bars + 16;
   uint64_t* dv_full = bars + 17;   // the last dV MMA has completed: the dV epilogue overlaps the last dQ / dK MMAs
+  uint64_t* qx_full = bars + 18;   // FOLD: the Q extension of the next tile is in shared memory (warp 15)
+  uint64_t* delta_full = bars + 19;   // FOLD: delta of the current tile is in shared memory (warp 15)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NUM_BARS);
 
   const float* lse2_ws = a.delta + (long long)a.B * a.H * a.Sqp;     // second half of the workspace: LSE_n * log2e
@@ -158,6 +172,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(do_full, 1); mbar_init(do_empty, 1);
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(ds_empty, 1);
     mbar_init(dq_full, 1); mbar_init(dq_empty, 128); mbar_init(dkv_full, 1); mbar_init(dv_full, 1);
+    mbar_init(qx_full, 1); mbar_init(delta_full, 1);
     fence_mbar_init();
     fence_proxy_async_smem();
     mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
@@ -167,11 +182,13 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tma_load_4d(sV + db * BLK_BYTES, &tm_v, kv_full, db * 64, k0, hk, b);
     }
     const int qi0 = i_start * 128;
-    mbar_arrive_expect_tx(&q_full[0], TILE_BYTES + 1024);
+    mbar_arrive_expect_tx(&q_full[0], TILE_BYTES + (FOLD ? 0 : 1024));
 #pragma unroll
     for (int db = 0; db < DB; ++db) tma_load_4d(sQ + db * BLK_BYTES, &tm_q, &q_full[0], db * 64, qi0, h, b);
-    bulk_load_1d(sLse, lse2_ws + (long long)bh * a.Sqp + qi0, 512, &q_full[0]);
-    bulk_load_1d(sDelta, a.delta + (long long)bh * a.Sqp + qi0, 512, &q_full[0]);
+    if constexpr (!FOLD) {
+      bulk_load_1d(sLse, lse2_ws + (long long)bh * a.Sqp + qi0, 512, &q_full[0]);
+      bulk_load_1d(sDelta, a.delta + (long long)bh * a.Sqp + qi0, 512, &q_full[0]);
+    }
     mbar_arrive_expect_tx(do_full, TILE_BYTES);
 #pragma unroll
     for (int db = 0; db < DB; ++db) tma_load_4d(sDO + db * BLK_BYTES, &tm_do, do_full, db * 64, qi0, h, b);
@@ -192,11 +209,13 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t ph = (it >> 1) & 1;
         const int qi0 = (i_start + it) * 128;
         mbar_wait(&q_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&q_full[s], TILE_BYTES + 1024);
+        mbar_arrive_expect_tx(&q_full[s], TILE_BYTES + (FOLD ? 0 : 1024));
 #pragma unroll
         for (int db = 0; db < DB; ++db) tma_load_4d(sQ + s * TILE_BYTES + db * BLK_BYTES, &tm_q, &q_full[s], db * 64, qi0, h, b);
-        bulk_load_1d(sLse + s * 128, lse2 + (long long)bh * a.Sqp + qi0, 512, &q_full[s]);
-        bulk_load_1d(sDelta + s * 128, a.delta + (long long)bh * a.Sqp + qi0, 512, &q_full[s]);
+        if constexpr (!FOLD) {
+          bulk_load_1d(sLse + s * 128, lse2 + (long long)bh * a.Sqp + qi0, 512, &q_full[s]);
+          bulk_load_1d(sDelta + s * 128, a.delta + (long long)bh * a.Sqp + qi0, 512, &q_full[s]);
+        }
         mbar_wait(do_empty, (it & 1) ^ 1);     // single dO buffer: free once dV of the previous tile has completed
         mbar_arrive_expect_tx(do_full, TILE_BYTES);
 #pragma unroll
@@ -219,6 +238,16 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t ds_km = umma_desc_lo(smem_u32(sDS), 16);
       const uint32_t k_mn = umma_desc_lo(smem_u32(sK), BLK_BYTES), q_mn = umma_desc_lo(smem_u32(sQ), BLK_BYTES);
       const uint32_t do_mn = umma_desc_lo(smem_u32(sDO), BLK_BYTES), ds_mn = umma_desc_lo(smem_u32(sDS), BLK_BYTES);
+      // FOLD: ninth K-step of S^T.  A = one core matrix of (w, w, w, 0, ...) rows serving all 128 kv rows (SBO = 0),
+      // B = the Q extension (row q: three-term 16-bit split of -LSE2[q] / (c * 2w)); the second 16-byte K-chunk of both
+      // aliases the first (LBO = 0), so the step adds 2w * (hi + lo + lo2) = -LSE2[q] / c to every element of column q.
+      const uint64_t ax_desc = umma_smem_desc_noswz(smem_u32(sAx), 0, 0), qx_desc = umma_smem_desc_noswz(smem_u32(sQx), 0, 128);
+      auto issue_fold = [&](int it_next) {
+        if constexpr (FOLD) {
+          mbar_wait(qx_full, it_next & 1);
+          tc_fence_after();
+        }
+      };
       auto issue_kmajor = [&](uint32_t tm_dst, uint32_t a_lo, uint32_t b_lo) {  // D[128x128] = A B^T over K = head dim
 #pragma unroll
         for (int kb = 0; kb < D / 16; ++kb) {
@@ -230,9 +259,14 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       TL_ONLY(lane == 0);
       mbar_wait(kv_full, 0);
       mbar_wait(&q_full[0], 0);
+      issue_fold(0);
       tc_fence_after();
       TL(1);
-      if (elect_one()) { issue_kmajor(TM_S, k_km, q_km); tc_commit(s_full); }
+      if (elect_one()) {
+        issue_kmajor(TM_S, k_km, q_km);
+        if constexpr (FOLD) umma_ss(tm + TM_S, ax_desc, qx_desc, idesc_kk, 1u);
+        tc_commit(s_full);
+      }
       __syncwarp();
       mbar_wait(do_full, 0);
       tc_fence_after();
@@ -259,9 +293,14 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // S^T of the next Q tile (overwrites P^T: ordered behind the dV MMAs on the tensor pipe)
         if (more) {
           mbar_wait(&q_full[s1], ph1);
+          issue_fold(it + 1);
           tc_fence_after();
           TL(3);
-          if (elect_one()) { issue_kmajor(TM_S, k_km, q_km + s1 * TILE16); tc_commit(s_full); }
+          if (elect_one()) {
+            issue_kmajor(TM_S, k_km, q_km + s1 * TILE16);
+            if constexpr (FOLD) umma_ss(tm + TM_S, ax_desc, qx_desc, idesc_kk, 1u);
+            tc_commit(s_full);
+          }
           __syncwarp();
         }
         // dQ_i = dS K first (its consumers, the reducer warps, then drain TMEM while dK executes) ;  dK += dS^T Q_i
@@ -298,6 +337,39 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       if (elect_one()) tc_commit(dkv_full);
       __syncwarp();
+    } else if (FOLD && warp == 15) {
+      // ---------------------------------------------------------------- FOLD: per-query constants
+      // LSE2 and delta of the next Q tile are fetched into registers ahead of time; the Q extension is rewritten as soon as
+      // the previous S^T MMA has read it (s_full), delta as soon as the compute warps are done with the previous tile (ds_full).
+      constexpr float W2 = BF16 ? 1.f : 256.f;                      // 2w: fp16 needs the range, bf16 does not
+      constexpr uint16_t av = BF16 ? 0x3F00 : 0x5800;               // w = 0.5 (bf16) / 128 (fp16)
+      const float inv = -1.f / (a.scale_log2 * W2);
+      if (lane < 8) *reinterpret_cast<uint4*>(sAx + lane * 16) = make_uint4(av | ((uint32_t)av << 16), av, 0u, 0u);
+      for (int it = 0; it < n_iter; ++it) {
+        const long long row0 = (long long)bh * a.Sqp + (i_start + it) * 128 + lane;
+        float l[4], d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { l[j] = __ldg(lse2_ws + row0 + j * 32); d[j] = __ldg(a.delta + row0 + j * 32); }
+        if (it > 0) mbar_wait(s_full, (it - 1) & 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // rows without a visible key and padding rows carry LSE2 = +inf: a large negative first term gives P = 0
+          const float x = (l[j] < 3.0e38f) ? l[j] * inv : (BF16 ? -1.0e30f : -30000.f);
+          const uint16_t h0 = (uint16_t)(pack2<BF16>(x, 0.f) & 0xFFFF);
+          const float r1 = (l[j] < 3.0e38f) ? x - cvt16_to_f32<BF16>(h0) : 0.f;
+          const uint16_t h1 = (uint16_t)(pack2<BF16>(r1, 0.f) & 0xFFFF);
+          const uint16_t h2 = (uint16_t)(pack2<BF16>(r1 - cvt16_to_f32<BF16>(h1), 0.f) & 0xFFFF);
+          *reinterpret_cast<uint4*>(sQx + (j * 32 + lane) * 16) = make_uint4(h0 | ((uint32_t)h1 << 16), h2, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(qx_full);
+        if (it > 0) mbar_wait(ds_full, (it - 1) & 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sDelta[j * 32 + lane] = d[j];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(delta_full);
+      }
     }
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ dQ reducers
@@ -444,7 +516,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mb0 = m0; mb1 = m1;
         }
       }
-      mbar_wait(&q_full[s], ph);          // LSE2 and delta of this tile have landed (same barrier as Q_i)
+      if constexpr (!FOLD) mbar_wait(&q_full[s], ph);          // LSE2 and delta of this tile have landed (same barrier as Q_i)
       mbar_wait(s_full, it & 1);
       tc_fence_after();
       TL(11);
@@ -456,7 +528,14 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_wait_ld();
       }
       const float* lse_s = sLse + s * 128 + half * 64;
-      if (has_aux) {
+      if constexpr (FOLD) {
+        // the tensor core has already subtracted LSE2 / c: P^T = 2^(c * S^T_aug)
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+          const float2 a01 = __fmul2_rn(make_float2(p[c], p[c + 1]), c2);
+          p[c] = ex2(a01.x); p[c + 1] = ex2(a01.y);
+        }
+      } else if (has_aux) {
         // generic path: bias added / mask applied in the log2 domain before the exponent
 #pragma unroll
         for (int c = 0; c < 64; c += 2) {
@@ -512,7 +591,8 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       TL(13);
       mbar_wait(ds_empty, (it & 1) ^ 1);  // MMAs of the previous iteration no longer read the dS^T tile
       TL(14);
-      const float* del_s = sDelta + s * 128 + half * 64;
+      if constexpr (FOLD) mbar_wait(delta_full, it & 1);
+      const float* del_s = sDelta + (FOLD ? 0 : s * 128) + half * 64;
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
         uint32_t dpr[32];
@@ -603,12 +683,12 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
 }  // namespace
 
-template <int D, bool BF16, bool CAUSAL, bool DROPOUT, bool AUX>
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT, bool AUX, bool FOLD = false>
 static cudaError_t launch_bwd_t2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
                                 const CUtensorMap& tdk, const CUtensorMap& tdv, const CUtensorMap& tdq, const BwdArgs& a, const TensorView& dk,
                                 const TensorView& dv, cudaStream_t stream) {
-  auto kern = fasn_bwd_kernel<D, BF16, CAUSAL, DROPOUT, AUX>;
-  constexpr int smem = BwdCfg<D>::SMEM_BYTES;
+  auto kern = fasn_bwd_kernel<D, BF16, CAUSAL, DROPOUT, AUX, FOLD>;
+  constexpr int smem = FOLD ? BwdCfg<D>::SMEM_BYTES_FOLD : BwdCfg<D>::SMEM_BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   dim3 grid(((a.Skv + 127) / 128) * a.B * a.H, 1, 1);
@@ -621,6 +701,11 @@ static cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, co
                                 const CUtensorMap& tdk, const CUtensorMap& tdv, const CUtensorMap& tdq, const BwdArgs& a, const TensorView& dk,
                                 const TensorView& dv, cudaStream_t stream) {
   const bool aux = a.bias.ptr != nullptr || a.alibi != nullptr || (a.mask.ptr != nullptr && a.mask.sq != 0);
+#if FASN_BWD_FOLD_LSE
+  // the fold divides by the logit scale: positive, normal scales only
+  if (!aux && a.scale_log2 > 1e-6f && a.scale_log2 < 1e6f)
+    return launch_bwd_t2<D, BF16, CAUSAL, DROPOUT, false, true>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv, stream);
+#endif
   return aux ? launch_bwd_t2<D, BF16, CAUSAL, DROPOUT, true>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv, stream)
              : launch_bwd_t2<D, BF16, CAUSAL, DROPOUT, false>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv, stream);
 }
