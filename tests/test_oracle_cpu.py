@@ -153,3 +153,20 @@ def test_dropout_generator_statistics():
     # different (seed, offset) streams are unrelated
     other = orc.dropout_keep_mask(0x5EED, 4, B, H, L, S, p).numpy().astype(np.float64) - rate
     assert abs((z * other).mean() / var) < 6.0 / np.sqrt(n)
+
+
+@pytest.mark.parametrize("dtype, w2", [(torch.float16, 256.0), (torch.bfloat16, 1.0)])
+def test_lse_fold_split_is_fp32_accurate(dtype, w2):
+    """Arithmetic of the experimental LSE2 fold (csrc/fasn_bwd.cu, FOLD): -LSE2 / c enters the S^T MMA as
+    2w * (hi + lo + lo2) with three 16-bit terms.  The reconstruction must leave the exponent c*S - LSE2 accurate to ~1e-5
+    (a 1e-5 relative error in P), far inside the 16-bit rounding of P itself."""
+    g = torch.Generator().manual_seed(5)
+    c = (1.0 / 128 ** 0.5) * 1.4426950408889634
+    lse2 = torch.empty(200000).uniform_(-8.0, 60.0, generator=g)
+    x = lse2 * (-1.0 / (c * w2))
+    h0 = x.to(dtype)
+    r1 = x - h0.float()
+    h1 = r1.to(dtype)
+    h2 = (r1 - h1.float()).to(dtype)
+    recon = w2 * (h0.float() + h1.float() + h2.float())            # what the tensor core adds to S (fp32 accumulation)
+    assert (recon.double() * c + lse2.double()).abs().max().item() < 1e-5
