@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "flash_attention_softmax_n", "libfasn.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["fasn_api.cu", "fasn_fwd.cu", "fasn_bwd.cu", "fasn_bwd2.cu", "fasn_bwd_aux.cu", "fasn_aux.cu", "fasn_softmax.cu"]
+SOURCES = ["fasn_api.cu", "fasn_fwd.cu", "fasn_bwd.cu", "fasn_bwd_aux.cu", "fasn_aux.cu", "fasn_softmax.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE]
 

@@ -2,10 +2,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
-#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <initializer_list>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -116,6 +116,8 @@ int check_common(const FasnParams* p) {
   }
   if (!(p->softmax_n >= 0.f)) return fail(FASN_EINVAL, "softmax_n must be >= 0");
   if (!(p->dropout_p >= 0.f && p->dropout_p < 1.f)) return fail(FASN_EINVAL, "dropout_p must be in [0,1)");
+  if (p->dropout_p > 0.f && lroundf((1.0f - p->dropout_p) * 256.0f) < 1)
+    return fail(FASN_EINVAL, "dropout_p %.6f quantises to keep probability 0 (the generator resolves 1/256)", (double)p->dropout_p);
   if (!std::isfinite(p->scale)) return fail(FASN_EINVAL, "scale must be finite");
   if (p->lse == nullptr) return fail(FASN_EINVAL, "lse is null");
   if (p->alibi_slopes != nullptr && p->bias.ptr != nullptr) return fail(FASN_EINVAL, "alibi_slopes and bias are mutually exclusive");
@@ -154,18 +156,16 @@ struct ScopedEvents {
 fasn::AuxView aux_view(const FasnAux& a) { return fasn::AuxView{a.ptr, a.stride_b, a.stride_h, a.stride_q}; }
 fasn::TensorView tensor_view(const FasnTensor& t) { return fasn::TensorView{t.ptr, t.stride_b, t.stride_h, t.stride_s}; }
 
-// backward main kernel: 0 = automatic, 1 = single-CTA (fasn_bwd.cu), 2 = CTA pair (fasn_bwd2.cu) where it applies
-#ifndef FASN_BWD_AUTO_PAIRED
-#define FASN_BWD_AUTO_PAIRED 0
-#endif
-std::atomic<int> g_bwd_impl{[] { const char* v = getenv("FASN_BWD_IMPL"); return (v != nullptr && v[0] >= '0' && v[0] <= '2') ? v[0] - '0' : 0; }()};
-
+// Dropout keeps an element iff an 8-bit uniform u < T, T = round(256 (1 - p)): the keep probability actually realised is
+// T / 256, and kept elements are scaled by its inverse 256 / T (not by 1 / (1 - p)), so that E[dropout(P)] = P exactly.
+// p < 1/512 quantises to T = 256 (nothing dropped, scale 1); p > 1 - 1/512 would quantise to T = 0 and is rejected.
 uint32_t keep_threshold(float dropout_p) {
   long t = lroundf((1.0f - dropout_p) * 256.0f);
   if (t < 0) t = 0;
   if (t > 256) t = 256;
   return (uint32_t)t;
 }
+float keep_probability(float dropout_p) { return dropout_p > 0.f ? (float)keep_threshold(dropout_p) / 256.0f : 1.0f; }
 
 
 }  // namespace
@@ -212,7 +212,7 @@ int fasn_fwd(const FasnParams* p) {
   a.bias = aux_view(p->bias);
   a.alibi = p->alibi_slopes;
   a.drop_thr = keep_threshold(p->dropout_p);
-  a.inv_keep = 1.0f / (1.0f - p->dropout_p);
+  a.inv_keep = 1.0f / keep_probability(p->dropout_p);
   a.key = fasn::make_philox_key(p->philox_seed, p->philox_offset, a.drop_thr);
   a.bh_offset = (uint32_t)p->bh_offset;
   a.sched_group = fasn::sched_group_size(2ll * D * (2ll * L + 2ll * S));            // Q, O, K, V of one unit
@@ -263,9 +263,9 @@ int fasn_bwd(const FasnParams* p) {
   fasn::BwdArgs a{};
   a.B = B; a.H = H; a.Hkv = Hkv; a.Sq = L; a.Skv = S;
   a.causal_off = S - L;
-  a.scale = p->scale / (1.0f - p->dropout_p);
+  a.scale = p->scale / keep_probability(p->dropout_p);
   a.scale_log2 = p->scale * fasn::kLog2e;
-  a.keep_prob = 1.0f - p->dropout_p;
+  a.keep_prob = keep_probability(p->dropout_p);
   a.lse = p->lse;
   a.delta = p->delta;
   a.dq_accum = p->dq_accum;
@@ -274,7 +274,7 @@ int fasn_bwd(const FasnParams* p) {
   a.bias = aux_view(p->bias);
   a.alibi = p->alibi_slopes;
   a.drop_thr = keep_threshold(p->dropout_p);
-  a.inv_keep = 1.0f / (1.0f - p->dropout_p);
+  a.inv_keep = 1.0f / keep_probability(p->dropout_p);
   a.key = fasn::make_philox_key(p->philox_seed, p->philox_offset, a.drop_thr);
   a.bh_offset = (uint32_t)p->bh_offset;
   a.sched_group = fasn::sched_group_size(2ll * D * (2ll * L + 2ll * S) + 4ll * D * L);   // Q, dO, K, V + the fp32 dQ accumulator
@@ -287,33 +287,14 @@ int fasn_bwd(const FasnParams* p) {
   cudaStream_t st = (cudaStream_t)p->stream;
   cudaError_t e = fasn::launch_bwd_prep(D, bf16, tensor_view(p->o), tensor_view(p->dout), a, st);
   if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd prep launch");
-  // Main kernel: the CTA-pair kernel (fasn_bwd2.cu) for head dim 128 without dense mask / bias, else the single-CTA
-  // kernel.  FASN_BWD_IMPL=1 in the environment forces the single-CTA kernel (A/B measurements, parity tests of both).
-  const int impl = g_bwd_impl.load();
-  const bool paired = (impl == 2 || (impl == 0 && FASN_BWD_AUTO_PAIRED)) && D == 128 && p->mask.ptr == nullptr && p->bias.ptr == nullptr &&
-                      p->alibi_slopes == nullptr;
-  CUtensorMap tq64, tdo64, tdq64;
-  if (paired) {
-    if (int rc = make_map(&tq64, p->q.ptr, p->q.stride_b, p->q.stride_h, p->q.stride_s, B, H, L, D, bf16, "q", 64)) return rc;
-    if (int rc = make_map(&tdo64, p->dout.ptr, p->dout.stride_b, p->dout.stride_h, p->dout.stride_s, B, H, L, D, bf16, "dout", 64)) return rc;
-    if (int rc = make_accum_map(&tdq64, p->dq_accum, (long long)B * H, (L + 127) / 128 * 128, D, 64)) return rc;
-  }
   {
     ScopedEvents prof(g_prof.bwd, st);
-    if (paired)
-      e = fasn::launch_bwd2(bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tq64, tk, tv, tdo, tdo64, tdk, tdv, tdq64, a, tensor_view(p->dk), tensor_view(p->dv), st);
-    else
-      e = fasn::launch_bwd(D, bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tk, tv, tdo, tdk, tdv, tdq, a, tensor_view(p->dk), tensor_view(p->dv), st);
+    e = fasn::launch_bwd(D, bf16, p->is_causal != 0, p->dropout_p > 0.f, tq, tk, tv, tdo, tdk, tdv, tdq, a, tensor_view(p->dk), tensor_view(p->dv), st);
   }
   if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd main launch");
   e = fasn::launch_bwd_finish(D, bf16, tensor_view(p->dq), a, st);
   if (e != cudaSuccess) return fail_cuda(e, "fasn_bwd finish launch");
   return 0;
-}
-
-int fasn_set_bwd_impl(int impl) {
-  if (impl < 0 || impl > 2) return fail(FASN_EINVAL, "fasn_set_bwd_impl: impl must be 0 (automatic), 1 (single-CTA kernel) or 2 (CTA-pair kernel)");
-  return g_bwd_impl.exchange(impl);
 }
 
 int fasn_profile(int enable) {
@@ -394,22 +375,12 @@ int fasn_softmax_n_bwd(const void* y, const void* dy, void* dx, int64_t rows, in
 }
 
 int fasn_probe(int mode, uint32_t dtype, const void* x, const void* y, float* c, void* stream) {
-  if (!((mode >= 0 && mode <= 6) || (mode >= 10 && mode <= 12)) || x == nullptr || y == nullptr || c == nullptr) return fail(FASN_EINVAL, "bad argument");
+  if (mode < 0 || mode > 4 || x == nullptr || y == nullptr || c == nullptr) return fail(FASN_EINVAL, "bad argument");
   if (dtype != FASN_FP16 && dtype != FASN_BF16) return fail(FASN_EUNSUPPORTED, "dtype");
   const bool bf16 = dtype == FASN_BF16;
   DeviceGuard guard(x);
   if (guard.err != cudaSuccess) return fail_cuda(guard.err, "x is not a device pointer / cannot bind its device");
   CUtensorMap tx, ty;
-  if (mode >= 10) {     // CTA-pair forms: x is 256x128, y is 128x128 (modes 10, 12) or 256x128 (mode 11)
-    const int yrows = mode == 11 ? 256 : 128;
-    CUtensorMap ty64;
-    if (int rc = make_map(&tx, x, 0, 0, 128, 1, 1, 256, 128, bf16, "x")) return rc;
-    if (int rc = make_map(&ty, y, 0, 0, 128, 1, 1, yrows, 128, bf16, "y")) return rc;
-    if (int rc = make_map(&ty64, y, 0, 0, 128, 1, 1, yrows, 128, bf16, "y", 64)) return rc;
-    cudaError_t e = fasn::launch_probe_pair(mode, bf16, tx, ty, ty64, x, c, (cudaStream_t)stream);
-    if (e != cudaSuccess) return fail_cuda(e, "fasn_probe (pair) launch");
-    return 0;
-  }
   if (int rc = make_map(&tx, x, 0, 0, 128, 1, 1, 128, 128, bf16, "x")) return rc;
   if (int rc = make_map(&ty, y, 0, 0, 128, 1, 1, 128, 128, bf16, "y")) return rc;
   cudaError_t e = fasn::launch_probe(mode, bf16, tx, ty, x, c, (cudaStream_t)stream);
@@ -421,12 +392,13 @@ int fasn_probe(int mode, uint32_t dtype, const void* x, const void* y, float* c,
 // host-buffer entry point (end-to-end measurement: H2D + kernels + D2H inside one call)
 // -------------------------------------------------------------------------------------------------
 namespace {
+// One device arena per device (keyed by the device that is current when fasn_attention_host is called), grown on demand.
 struct Arena {
   void* base = nullptr;
   size_t cap = 0;
-  std::mutex mu;
 };
-Arena g_arena;
+std::mutex g_arena_mu;
+std::map<int, Arena> g_arenas;
 }  // namespace
 
 int fasn_attention_host(uint32_t dtype, int32_t batch, int32_t heads, int32_t seqlen_q, int32_t seqlen_kv, int32_t head_dim,
@@ -452,7 +424,10 @@ int fasn_attention_host(uint32_t dtype, int32_t batch, int32_t heads, int32_t se
     o_do = take(nq); o_dq = take(nq); o_dk = take(nkv); o_dv = take(nkv); o_delta = take(2 * BH * Lp * 4);
     o_acc = take(BH * Lp * head_dim * 4);
   }
-  std::lock_guard<std::mutex> lock(g_arena.mu);
+  int dev = 0;
+  if (cudaError_t e0 = cudaGetDevice(&dev); e0 != cudaSuccess) return fail_cuda(e0, "cudaGetDevice");
+  std::lock_guard<std::mutex> lock(g_arena_mu);
+  Arena& g_arena = g_arenas[dev];
   if (g_arena.cap < off) {
     if (g_arena.base) cudaFree(g_arena.base);
     g_arena.base = nullptr; g_arena.cap = 0;

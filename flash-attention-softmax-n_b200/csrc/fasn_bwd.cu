@@ -18,7 +18,12 @@
 // The only difference from softmax_0 attention is that P is recomputed from LSE_n = ln(n + sum exp s) (SURVEY.md
 // section 9): the Jacobian keeps the softmax form dS = P o (dP - delta) with delta_i = sum_d O_id dO_id.
 //
-//   warps 0-7   compute: warp w owns TMEM lanes 32(w%4).. (kv rows) and q-columns 64(w/4)..64(w/4)+63
+//   warps 0-7   compute: warp w owns TMEM lanes 32(w%4).. (kv rows) and q-columns 64(w/4)..64(w/4)+63.  Inside the warp
+//               the fast kernels use the "quad" register layout of tcgen05.ld.16x256b: a thread holds 4 kv rows x 16
+//               query columns (not 1 row x 64 columns), so it needs LSE2 / delta of 16 queries per tile instead of 64
+//               and the four threads of a quad fetch them with one 32-byte shared-memory wavefront -- the per-query
+//               constants cost 16 wavefronts per warp and tile instead of 128 (they were 950 of the ~5300 shared-memory
+//               port cycles per tile pair)
 //   warps 8-11  dQ reducers: TMEM -> registers -> fp32 staging in smem -> TMA reduce-add
 //   warp 12     TMA producer (K,V once; Q_i + LSE2 + delta through a 2-deep ring, dO_i single-buffered)
 //   warp 13     MMA issuer (one elected lane)  warp 14  TMEM allocator        warp 15  idle
@@ -41,14 +46,6 @@ namespace {
 #define TL(tag)
 #endif
 
-#ifndef FASN_DQ_DIRECT
-#define FASN_DQ_DIRECT 0
-#endif
-// Experimental (not the default): fold -LSE2 into the S^T MMA as a ninth K-step instead of
-// delivering it to every compute thread through uniform-address shared-memory loads.
-#ifndef FASN_BWD_FOLD_LSE
-#define FASN_BWD_FOLD_LSE 0
-#endif
 
 constexpr int kBwdThreads = 512;
 
@@ -57,13 +54,10 @@ template <int D> struct BwdCfg {
   static constexpr int TILE_BYTES = 128 * D * 2;
   static constexpr int BLK_BYTES = 128 * 128;
   static constexpr int DS_BYTES = 2 * BLK_BYTES;                  // dS^T: [2 q-blocks][128 kv rows][128 B]
-  static constexpr int NUM_BARS = 20;
+  static constexpr int NUM_BARS = 18;
   static constexpr int DQ_STAGE_BYTES = 128 * 32 * 4;             // dQ staging chunk: 128 rows x 32 fp32 columns
   // K, V, Q ring (2), dO (1), dS^T, dQ staging (2 chunks), LSE2 ring + delta ring (2 x 2 x 512 B), barriers, tmem slot
   static constexpr int SMEM_BYTES = 5 * TILE_BYTES + DS_BYTES + 2 * DQ_STAGE_BYTES + 4 * 512 + NUM_BARS * 8 + 16;
-  // FOLD: Q-tile extension (128 rows x 16 B), K-side extension (one 128-byte core matrix), delta (single buffer), barriers
-  static constexpr int QX_BYTES = 128 * 16, AX_BYTES = 128;
-  static constexpr int SMEM_BYTES_FOLD = 5 * TILE_BYTES + DS_BYTES + 2 * DQ_STAGE_BYTES + QX_BYTES + AX_BYTES + 512 + NUM_BARS * 8 + 16;
 };
 
 // TMA reduce-add shared -> global (fp32 tile added into the tensor at L2), bulk async-group completion
@@ -85,7 +79,7 @@ FASN_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, 
 
 // AUX = true: dense attn_mask / attn_bias tensors (generic path); AUX = false keeps that code out of the fast kernels
 // (a key-padding mask with row stride 0 is handled by both).
-template <int D, bool BF16, bool CAUSAL, bool DROPOUT, bool AUX, bool FOLD = false>
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT, bool AUX>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -93,7 +87,6 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const __grid_constant__ CUtensorMap tm_dq, const BwdArgs a,
                 const TensorView dk_view, const TensorView dv_view) {
   using Cfg = BwdCfg<D>;
-  static_assert(!(FOLD && AUX), "the LSE2 fold is built for the fast kernels only");
   constexpr int DB = Cfg::DB, TILE_BYTES = Cfg::TILE_BYTES, BLK_BYTES = Cfg::BLK_BYTES;
   constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 128, TM_DV = 256, TM_DK = 256 + D;
 
@@ -137,12 +130,9 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint8_t* sDO = sQ + 2 * TILE_BYTES;         // [1]
   uint8_t* sDS = sDO + TILE_BYTES;
   uint8_t* sDQ = sDS + Cfg::DS_BYTES;         // [2] fp32 staging chunks for the TMA reduce-add of dQ
-  // FOLD: [Q extension 2 KB][K-side extension 128 B][delta, single buffer 512 B] instead of the LSE2 and delta rings
-  uint8_t* sQx = sDQ + 2 * Cfg::DQ_STAGE_BYTES;
-  uint8_t* sAx = sQx + Cfg::QX_BYTES;
   float* sLse = reinterpret_cast<float*>(sDQ + 2 * Cfg::DQ_STAGE_BYTES);   // [2][128]
-  float* sDelta = FOLD ? reinterpret_cast<float*>(sAx + Cfg::AX_BYTES) : sLse + 256;   // [2][128] ([128] with FOLD)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + (FOLD ? 128 : 256));
+  float* sDelta = sLse + 256;                                              // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
   uint64_t* kv_full = bars + 0;
   uint64_t* q_full = bars + 1;     // [2]
   uint64_t* q_empty = bars + 3;    // [2]
@@ -157,8 +147,6 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* dq_empty = bars + 15;  // 128 arrivals
   uint64_t* dkv_full = bars + 16;
   uint64_t* dv_full = bars + 17;   // the last dV MMA has completed: the dV epilogue overlaps the last dQ / dK MMAs
-  uint64_t* qx_full = bars + 18;   // FOLD: the Q extension of the next tile is in shared memory (warp 15)
-  uint64_t* delta_full = bars + 19;   // FOLD: delta of the current tile is in shared memory (warp 15)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NUM_BARS);
 
   const float* lse2_ws = a.delta + (long long)a.B * a.H * a.Sqp;     // second half of the workspace: LSE_n * log2e
@@ -172,7 +160,6 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(do_full, 1); mbar_init(do_empty, 1);
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(ds_empty, 1);
     mbar_init(dq_full, 1); mbar_init(dq_empty, 128); mbar_init(dkv_full, 1); mbar_init(dv_full, 1);
-    mbar_init(qx_full, 1); mbar_init(delta_full, 1);
     fence_mbar_init();
     fence_proxy_async_smem();
     mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
@@ -182,13 +169,11 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tma_load_4d(sV + db * BLK_BYTES, &tm_v, kv_full, db * 64, k0, hk, b);
     }
     const int qi0 = i_start * 128;
-    mbar_arrive_expect_tx(&q_full[0], TILE_BYTES + (FOLD ? 0 : 1024));
+    mbar_arrive_expect_tx(&q_full[0], TILE_BYTES + 1024);
 #pragma unroll
     for (int db = 0; db < DB; ++db) tma_load_4d(sQ + db * BLK_BYTES, &tm_q, &q_full[0], db * 64, qi0, h, b);
-    if constexpr (!FOLD) {
-      bulk_load_1d(sLse, lse2_ws + (long long)bh * a.Sqp + qi0, 512, &q_full[0]);
-      bulk_load_1d(sDelta, a.delta + (long long)bh * a.Sqp + qi0, 512, &q_full[0]);
-    }
+    bulk_load_1d(sLse, lse2_ws + (long long)bh * a.Sqp + qi0, 512, &q_full[0]);
+    bulk_load_1d(sDelta, a.delta + (long long)bh * a.Sqp + qi0, 512, &q_full[0]);
     mbar_arrive_expect_tx(do_full, TILE_BYTES);
 #pragma unroll
     for (int db = 0; db < DB; ++db) tma_load_4d(sDO + db * BLK_BYTES, &tm_do, do_full, db * 64, qi0, h, b);
@@ -209,13 +194,11 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t ph = (it >> 1) & 1;
         const int qi0 = (i_start + it) * 128;
         mbar_wait(&q_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&q_full[s], TILE_BYTES + (FOLD ? 0 : 1024));
+        mbar_arrive_expect_tx(&q_full[s], TILE_BYTES + 1024);
 #pragma unroll
         for (int db = 0; db < DB; ++db) tma_load_4d(sQ + s * TILE_BYTES + db * BLK_BYTES, &tm_q, &q_full[s], db * 64, qi0, h, b);
-        if constexpr (!FOLD) {
-          bulk_load_1d(sLse + s * 128, lse2 + (long long)bh * a.Sqp + qi0, 512, &q_full[s]);
-          bulk_load_1d(sDelta + s * 128, a.delta + (long long)bh * a.Sqp + qi0, 512, &q_full[s]);
-        }
+        bulk_load_1d(sLse + s * 128, lse2 + (long long)bh * a.Sqp + qi0, 512, &q_full[s]);
+        bulk_load_1d(sDelta + s * 128, a.delta + (long long)bh * a.Sqp + qi0, 512, &q_full[s]);
         mbar_wait(do_empty, (it & 1) ^ 1);     // single dO buffer: free once dV of the previous tile has completed
         mbar_arrive_expect_tx(do_full, TILE_BYTES);
 #pragma unroll
@@ -238,16 +221,6 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t ds_km = umma_desc_lo(smem_u32(sDS), 16);
       const uint32_t k_mn = umma_desc_lo(smem_u32(sK), BLK_BYTES), q_mn = umma_desc_lo(smem_u32(sQ), BLK_BYTES);
       const uint32_t do_mn = umma_desc_lo(smem_u32(sDO), BLK_BYTES), ds_mn = umma_desc_lo(smem_u32(sDS), BLK_BYTES);
-      // FOLD: ninth K-step of S^T.  A = one core matrix of (w, w, w, 0, ...) rows serving all 128 kv rows (SBO = 0),
-      // B = the Q extension (row q: three-term 16-bit split of -LSE2[q] / (c * 2w)); the second 16-byte K-chunk of both
-      // aliases the first (LBO = 0), so the step adds 2w * (hi + lo + lo2) = -LSE2[q] / c to every element of column q.
-      const uint64_t ax_desc = umma_smem_desc_noswz(smem_u32(sAx), 0, 0), qx_desc = umma_smem_desc_noswz(smem_u32(sQx), 0, 128);
-      auto issue_fold = [&](int it_next) {
-        if constexpr (FOLD) {
-          mbar_wait(qx_full, it_next & 1);
-          tc_fence_after();
-        }
-      };
       auto issue_kmajor = [&](uint32_t tm_dst, uint32_t a_lo, uint32_t b_lo) {  // D[128x128] = A B^T over K = head dim
 #pragma unroll
         for (int kb = 0; kb < D / 16; ++kb) {
@@ -259,12 +232,10 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       TL_ONLY(lane == 0);
       mbar_wait(kv_full, 0);
       mbar_wait(&q_full[0], 0);
-      issue_fold(0);
       tc_fence_after();
       TL(1);
       if (elect_one()) {
         issue_kmajor(TM_S, k_km, q_km);
-        if constexpr (FOLD) umma_ss(tm + TM_S, ax_desc, qx_desc, idesc_kk, 1u);
         tc_commit(s_full);
       }
       __syncwarp();
@@ -293,12 +264,10 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // S^T of the next Q tile (overwrites P^T: ordered behind the dV MMAs on the tensor pipe)
         if (more) {
           mbar_wait(&q_full[s1], ph1);
-          issue_fold(it + 1);
           tc_fence_after();
           TL(3);
           if (elect_one()) {
             issue_kmajor(TM_S, k_km, q_km + s1 * TILE16);
-            if constexpr (FOLD) umma_ss(tm + TM_S, ax_desc, qx_desc, idesc_kk, 1u);
             tc_commit(s_full);
           }
           __syncwarp();
@@ -337,39 +306,6 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       if (elect_one()) tc_commit(dkv_full);
       __syncwarp();
-    } else if (FOLD && warp == 15) {
-      // ---------------------------------------------------------------- FOLD: per-query constants
-      // LSE2 and delta of the next Q tile are fetched into registers ahead of time; the Q extension is rewritten as soon as
-      // the previous S^T MMA has read it (s_full), delta as soon as the compute warps are done with the previous tile (ds_full).
-      constexpr float W2 = BF16 ? 1.f : 256.f;                      // 2w: fp16 needs the range, bf16 does not
-      constexpr uint16_t av = BF16 ? 0x3F00 : 0x5800;               // w = 0.5 (bf16) / 128 (fp16)
-      const float inv = -1.f / (a.scale_log2 * W2);
-      if (lane < 8) *reinterpret_cast<uint4*>(sAx + lane * 16) = make_uint4(av | ((uint32_t)av << 16), av, 0u, 0u);
-      for (int it = 0; it < n_iter; ++it) {
-        const long long row0 = (long long)bh * a.Sqp + (i_start + it) * 128 + lane;
-        float l[4], d[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { l[j] = __ldg(lse2_ws + row0 + j * 32); d[j] = __ldg(a.delta + row0 + j * 32); }
-        if (it > 0) mbar_wait(s_full, (it - 1) & 1);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          // rows without a visible key and padding rows carry LSE2 = +inf: a large negative first term gives P = 0
-          const float x = (l[j] < 3.0e38f) ? l[j] * inv : (BF16 ? -1.0e30f : -30000.f);
-          const uint16_t h0 = (uint16_t)(pack2<BF16>(x, 0.f) & 0xFFFF);
-          const float r1 = (l[j] < 3.0e38f) ? x - cvt16_to_f32<BF16>(h0) : 0.f;
-          const uint16_t h1 = (uint16_t)(pack2<BF16>(r1, 0.f) & 0xFFFF);
-          const uint16_t h2 = (uint16_t)(pack2<BF16>(r1 - cvt16_to_f32<BF16>(h1), 0.f) & 0xFFFF);
-          *reinterpret_cast<uint4*>(sQx + (j * 32 + lane) * 16) = make_uint4(h0 | ((uint32_t)h1 << 16), h2, 0u, 0u);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(qx_full);
-        if (it > 0) mbar_wait(ds_full, (it - 1) & 1);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sDelta[j * 32 + lane] = d[j];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(delta_full);
-      }
     }
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ dQ reducers
@@ -381,35 +317,6 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     constexpr int NCH = D / 32;                           // 32-column chunks per dQ tile
     TL_DECL(3)
     TL_ONLY(threadIdx.x == 256);
-#if FASN_DQ_DIRECT
-    // Direct variant: tcgen05.ld shape 16x256b puts 32 contiguous bytes of a dQ row into each quad of lanes, so one
-    // red.global.add.v2.f32 per thread adds whole 32-byte sectors at the L2 -- no shared-memory staging (the staged TMA
-    // reduce costs 128 KB of shared-memory traffic per Q tile in a kernel that is bound by that port).
-    const int g = lane >> 2, t2 = (lane & 3) * 2;
-    for (int it = 0; it < n_iter; ++it) {
-      const int qi0 = (i_start + it) * 128;
-      float* dst = a.dq_accum + ((long long)bh * a.Sqp + qi0 + (warp & 3) * 32 + g) * D + t2;
-      mbar_wait(dq_full, it & 1);
-      tc_fence_after();
-      TL(30);
-#pragma unroll
-      for (int hb = 0; hb < D / 64; ++hb) {
-        uint32_t v[64];
-        tmem_ld_16x256b_x8(tmem_base + lane_off + TM_DQ + hb * 64, v);
-        tmem_ld_16x256b_x8(tmem_base + lane_off + (16u << 16) + TM_DQ + hb * 64, v + 32);
-        tmem_wait_ld();
-        if (hb == D / 64 - 1) { tc_fence_before(); mbar_arrive(dq_empty); TL(31); }
-#pragma unroll
-        for (int h16 = 0; h16 < 2; ++h16)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float* p0 = dst + (h16 * 16) * D + hb * 64 + c * 8;
-            red_add_v2(p0, __uint_as_float(v[h16 * 32 + 4 * c]), __uint_as_float(v[h16 * 32 + 4 * c + 1]));
-            red_add_v2(p0 + 8 * D, __uint_as_float(v[h16 * 32 + 4 * c + 2]), __uint_as_float(v[h16 * 32 + 4 * c + 3]));
-          }
-      }
-    }
-#else
     for (int it = 0; it < n_iter; ++it) {
       const int qi0 = (i_start + it) * 128;
       mbar_wait(dq_full, it & 1);
@@ -422,7 +329,6 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld_x32(tmem_base + lane_off + TM_DQ + hb * 64 + 32, v + 32);
         tmem_wait_ld();
         if (hb == NCH / 2 - 1) { tc_fence_before(); mbar_arrive(dq_empty); TL(31); }   // dQ columns may be overwritten by dP^T now
-#ifndef FASN_EXP_NO_DQ
         if (threadIdx.x == 256) tma_store_wait_read<0>();   // the previous round's reduces have read both staging chunks
         named_bar_sync(2, 128);
 #pragma unroll
@@ -438,196 +344,327 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tma_reduce_add_4d(&tm_dq, sDQ + Cfg::DQ_STAGE_BYTES, hb * 64 + 32, qi0, bh, 0);
           tma_store_commit();
         }
-#endif
       }
     }
-#endif
     if (threadIdx.x == 256) tma_store_wait_all();
   } else {
     // -------------------------------------------------------------------- compute warps
     setmaxnreg_inc<176>();
     const int quarter = warp & 3;
     const int half = warp >> 2;
-    const int r = quarter * 32 + lane;                     // kv row inside the tile
-    const int kv_row = k0 + r;
+    const int r = quarter * 32 + lane;                     // kv row inside the tile (row layout: AUX loop, epilogue)
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const int kv_c = min(kv_row, a.Skv - 1);
-    const uint8_t* mbase = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr) + b * a.mask.sb + h * a.mask.sh + kv_c : nullptr;
-    // A mask that is broadcast over the query axis (key padding, (B|1, H|1, 1, S)) is one byte per key: this thread's
-    // key is either visible to every query or to none, which the fast path handles like a row beyond Skv.
-    const bool key_only_mask = (mbase != nullptr) && (a.mask.sq == 0);
-    const bool key_masked = key_only_mask && (*mbase == 0);
-    if (key_only_mask) mbase = nullptr;
-    const bool kv_valid = (kv_row < a.Skv) && !key_masked;
-    const bool has_aux = AUX && ((mbase != nullptr) || (a.bias.ptr != nullptr) || (a.alibi != nullptr));
-    const float alibi2 = (AUX && a.alibi != nullptr) ? a.alibi[h] * kLog2e : 0.f;
-    const uint16_t* bbase = a.bias.ptr ? reinterpret_cast<const uint16_t*>(a.bias.ptr) + b * a.bias.sb + h * a.bias.sh + kv_c : nullptr;
+    const uint8_t* mask_bh = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr) + b * a.mask.sb + h * a.mask.sh : nullptr;
+    // A mask that is broadcast over the query axis (key padding, (B|1, H|1, 1, S)) is one byte per key: a key is either
+    // visible to every query or to none, which the fast path handles like a row beyond Skv.
+    const bool key_only_mask = (mask_bh != nullptr) && (a.mask.sq == 0);
     const uint32_t bh_global = a.bh_offset + bh;
-    const uint32_t kvw = (uint32_t)(kv_row >> 5);          // identical for the 32 lanes of this warp
-
+    const uint32_t kvw = (uint32_t)((k0 + quarter * 32) >> 5);   // 32-key word index of this warp's kv rows
     const bool kv_tail = (k0 + 128 > a.Skv) || key_only_mask;   // this K/V tile (may) have rows that no query sees
     TL_DECL(1 + half)
     TL_ONLY(threadIdx.x == 0 || threadIdx.x == 128);
     const float2 c2 = make_float2(a.scale_log2, a.scale_log2);
 
-    // Dropout keep bits: lane L generates the 32-key keep words of query rows qc0+L and qc0+32+L; a 32x32 bit
-    // transpose across the warp then hands every lane (= kv row) its own bit of all 64 query columns.
-    uint32_t keep_next0 = 0xFFFFFFFFu, keep_next1 = 0xFFFFFFFFu;
-    auto make_keep = [&](int qc0n) {
-      if constexpr (DROPOUT) {
-        keep_next0 = warp_transpose_bits(dropout_keep_word(a.key, bh_global, (uint32_t)(qc0n + lane), kvw, a.drop_thr), lane);
-        keep_next1 = warp_transpose_bits(dropout_keep_word(a.key, bh_global, (uint32_t)(qc0n + 32 + lane), kvw, a.drop_thr), lane);
+    if constexpr (!AUX) {
+      // ---------------------------------------------------------------- fast kernels: quad layout
+      // tcgen05.ld.16x256b hands thread (g = lane / 4, t4 = lane % 4) the kv rows 8 j + g (j = 0..3) of this warp's 32 and
+      // the query columns 8 c + 2 t4 + {0, 1} (c = 0..7) of its 64:  v[32 (j / 2) + 4 c + 2 (j % 2) + e].  The packed 16-bit
+      // pairs go back to tensor memory with tcgen05.st.16x128b (column 4 c + t4 of the 32 packed columns), and into the
+      // dS^T tile with 4-byte stores that are conflict-free under the 128-byte swizzle (8 rows x 4 lanes = 32 banks).
+      const int g = lane >> 2, t4 = lane & 3;
+      int rowpad[4];                                       // 0 for a real, visible key; 64 pushes the row's first visible column out of the tile
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kvr = k0 + quarter * 32 + 8 * j + g;
+        bool valid = kvr < a.Skv;
+        if (key_only_mask && valid) valid = mask_bh[kvr] != 0;
+        rowpad[j] = valid ? 0 : 64;
       }
-    };
-    make_keep(i_start * 128 + half * 64);
+      // Dropout keep words: lane L generates the 32-key words of query rows qc0 + L and qc0 + 32 + L one iteration ahead
+      // (in the slot where this warp would otherwise wait for dP^T); each thread then fetches the words of its 16 query
+      // columns with shuffles and shifts them so that the bit of kv row 8 j + g sits in the sign position of byte j.
+      uint32_t keep_raw0 = 0xFFFFFFFFu, keep_raw1 = 0xFFFFFFFFu;
+      auto make_keep = [&](int qc0n) {
+        if constexpr (DROPOUT) {
+          keep_raw0 = dropout_keep_word(a.key, bh_global, (uint32_t)(qc0n + lane), kvw, a.drop_thr);
+          keep_raw1 = dropout_keep_word(a.key, bh_global, (uint32_t)(qc0n + 32 + lane), kvw, a.drop_thr);
+        }
+      };
+      make_keep(i_start * 128 + half * 64);
+      uint8_t* const ds_base = sDS + half * BLK_BYTES + (quarter * 32 + g) * 128 + 4 * t4;
 
-    for (int it = 0; it < n_iter; ++it) {
-      const int s = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
-      const int qi0 = (i_start + it) * 128;
-      const int qc0 = qi0 + half * 64;                     // first query column of this thread
-      // keep0 / keep1: bit c = keep decision for (query qc0 + c [+32], this thread's kv row); generated one
-      // iteration ahead (below), in the slot where this warp would otherwise wait for dP^T
-      const uint32_t keep0 = keep_next0, keep1 = keep_next1;
-      // ---- P^T = 2^(S^T c - LSE2)
-      TL(10);
-      // Dense bias / mask (generic path): this thread needs one column of the (L, S) matrix -- its key, 64 queries.  The
-      // 32 lanes of a warp read 32 consecutive keys, so each load instruction is one coalesced 64-byte segment; all 64
-      // (+64) loads are independent of S^T and are issued here, before the wait for the tensor core, so their latency
-      // overlaps it.  Rows beyond Sq are clamped (their P is 0 anyway: LSE2 = +inf on padding rows).
-      uint32_t bpk[AUX ? 32 : 1];
-      uint32_t mb0 = 0xFFFFFFFFu, mb1 = 0xFFFFFFFFu;
-      if constexpr (AUX) if (has_aux) {
-        if (bbase) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int qi0 = (i_start + it) * 128;
+        const int qc0 = qi0 + half * 64;                   // first query column of this warp
+        TL(10);
+        uint32_t kx[DROPOUT ? 16 : 1];                     // kx[2 c + e]: keep word of query column 8 c + 2 t4 + e, shifted left by 7 - g
+        if constexpr (DROPOUT) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              kx[DROPOUT ? 2 * c + e : 0] = __shfl_sync(0xffffffffu, (c < 4) ? keep_raw0 : keep_raw1, ((c & 3) << 3) + 2 * t4 + e) << (7 - g);
+        }
+        // ---- P^T = 2^(S^T c - LSE2)
+        mbar_wait(&q_full[s], ph);                         // LSE2 and delta of this tile have landed (same barrier as Q_i)
+        mbar_wait(s_full, it & 1);
+        tc_fence_after();
+        TL(11);
+        float p[64];
+        {
+          uint32_t* pr = reinterpret_cast<uint32_t*>(p);
+          tmem_ld_16x256b_x8(tmem_base + lane_off + TM_S + half * 64, pr);
+          tmem_ld_16x256b_x8(tmem_base + lane_off + (16u << 16) + TM_S + half * 64, pr + 32);
+          tmem_wait_ld();
+        }
+        const float* lse_s = sLse + s * 128 + half * 64 + 2 * t4;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float2 l2 = *reinterpret_cast<const float2*>(lse_s + 8 * c);
+          const float2 nl = make_float2(-l2.x, -l2.y);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int idx = (j >> 1) * 32 + 4 * c + 2 * (j & 1);
+            const float2 a01 = __ffma2_rn(make_float2(p[idx], p[idx + 1]), c2, nl);
+            p[idx] = ex2(a01.x); p[idx + 1] = ex2(a01.y);
+          }
+        }
+        const bool diag = CAUSAL && (qi0 + a.causal_off < k0 + 127);     // some (q, kv) of this tile pair lies above the diagonal
+        if (diag || kv_tail) {
+          // query column x of this warp's 64 is visible to kv row kvr iff kvr <= q + off  <=>  x >= kvr - off - qc0;
+          // x = 8 c + 2 t4 + e, so the compile-time part 8 c + e is compared with a per-row threshold
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int kvr = k0 + quarter * 32 + 8 * j + g;
+            const int fc = (diag ? max(kvr - a.causal_off - qc0, 0) : 0) + rowpad[j] - 2 * t4;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int idx = (j >> 1) * 32 + 4 * c + 2 * (j & 1) + e;
+                p[idx] = (8 * c + e >= fc) ? p[idx] : 0.f;
+              }
+          }
+        }
+#pragma unroll
+        for (int h16 = 0; h16 < 2; ++h16) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int idx = h16 * 32 + 4 * c + 2 * u;
+              uint32_t w01 = pack2<BF16>(p[idx], p[idx + 1]);
+              // dropped entries are zeroed on the packed pair (1 PRMT + 1 AND per two elements); the 1/(1-p) factor of the
+              // kept entries is applied to dV in the epilogue
+              if constexpr (DROPOUT) w01 &= keep_byte_pair_mask(kx[DROPOUT ? 2 * c : 0], kx[DROPOUT ? 2 * c + 1 : 0], 2 * h16 + u);
+              pk[2 * c + u] = w01;
+            }
+          tmem_st_16x128b_x8(tmem_base + lane_off + (static_cast<uint32_t>(h16 * 16) << 16) + TM_S + half * 64, pk);   // over S^T columns this warp has read
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(p_full);
+        TL(12);
+        if (it + 1 < n_iter) make_keep(qc0 + 128);          // next tile's keep words, while dP^T is still in flight
+        // ---- dS'^T = P^T o (Z dP^T - (1-p) delta)      (dS = dS' / (1-p); the factor is folded into the dK / dQ scales)
+        const float* del_s = sDelta + s * 128 + half * 64 + 2 * t4;
+        float2 nd[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float2 d2 = *reinterpret_cast<const float2*>(del_s + 8 * c);
+          nd[c] = make_float2(-d2.x, -d2.y);
+        }
+        mbar_wait(dp_full, it & 1);
+        tc_fence_after();
+        TL(13);
+        mbar_wait(ds_empty, (it & 1) ^ 1);  // MMAs of the previous iteration no longer read the dS^T tile
+        TL(14);
+#pragma unroll
+        for (int h16 = 0; h16 < 2; ++h16) {
+          uint32_t dpr[32];
+          tmem_ld_16x256b_x8(tmem_base + lane_off + (static_cast<uint32_t>(h16 * 16) << 16) + TM_DP + half * 64, dpr);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t choff = static_cast<uint32_t>((c ^ g) << 4);      // 16-byte chunk c of the row under the 128B swizzle (row & 7 == g)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int j = 2 * h16 + u, idx = 4 * c + 2 * u;
+              float dp0 = __uint_as_float(dpr[idx]), dp1 = __uint_as_float(dpr[idx + 1]);
+              if constexpr (DROPOUT) {
+                dp0 = (kx[DROPOUT ? 2 * c : 0] & (0x80u << (8 * j))) ? dp0 : 0.f;
+                dp1 = (kx[DROPOUT ? 2 * c + 1 : 0] & (0x80u << (8 * j))) ? dp1 : 0.f;
+              }
+              const float2 e01 = __fadd2_rn(make_float2(dp0, dp1), nd[c]);
+              const float2 s01 = __fmul2_rn(make_float2(p[h16 * 32 + idx], p[h16 * 32 + idx + 1]), e01);
+              *reinterpret_cast<uint32_t*>(ds_base + j * (8 * 128) + choff) = pack2<BF16>(s01.x, s01.y);
+            }
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(ds_full);
+        TL(15);
+      }
+    } else {
+      // ---------------------------------------------------------------- dense mask / bias / ALiBi kernels: row layout
+      // (thread = one kv row x 64 query columns: its bias / mask elements are one coalesced 64-byte segment per load)
+      const int kv_row = k0 + r;
+      const int kv_c = min(kv_row, a.Skv - 1);
+      const uint8_t* mbase = (mask_bh != nullptr && !key_only_mask) ? mask_bh + kv_c : nullptr;
+      const bool key_masked = key_only_mask && (mask_bh[kv_c] == 0);
+      const bool kv_valid = (kv_row < a.Skv) && !key_masked;
+      const bool has_aux = (mbase != nullptr) || (a.bias.ptr != nullptr) || (a.alibi != nullptr);
+      const float alibi2 = (a.alibi != nullptr) ? a.alibi[h] * kLog2e : 0.f;
+      const uint16_t* bbase = a.bias.ptr ? reinterpret_cast<const uint16_t*>(a.bias.ptr) + b * a.bias.sb + h * a.bias.sh + kv_c : nullptr;
+      // Dropout keep bits: lane L generates the 32-key keep words of query rows qc0+L and qc0+32+L; a 32x32 bit
+      // transpose across the warp then hands every lane (= kv row) its own bit of all 64 query columns.
+      uint32_t keep_next0 = 0xFFFFFFFFu, keep_next1 = 0xFFFFFFFFu;
+      auto make_keep = [&](int qc0n) {
+        if constexpr (DROPOUT) {
+          keep_next0 = warp_transpose_bits(dropout_keep_word(a.key, bh_global, (uint32_t)(qc0n + lane), kvw, a.drop_thr), lane);
+          keep_next1 = warp_transpose_bits(dropout_keep_word(a.key, bh_global, (uint32_t)(qc0n + 32 + lane), kvw, a.drop_thr), lane);
+        }
+      };
+      make_keep(i_start * 128 + half * 64);
+
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const int qi0 = (i_start + it) * 128;
+        const int qc0 = qi0 + half * 64;                     // first query column of this thread
+        // keep0 / keep1: bit c = keep decision for (query qc0 + c [+32], this thread's kv row); generated one
+        // iteration ahead (below), in the slot where this warp would otherwise wait for dP^T
+        const uint32_t keep0 = keep_next0, keep1 = keep_next1;
+        // ---- P^T = 2^(S^T c + bias - LSE2)
+        TL(10);
+        // This thread needs one column of the (L, S) matrix -- its key, 64 queries.  The 32 lanes of a warp read 32
+        // consecutive keys, so each load instruction is one coalesced 64-byte segment; all 64 (+64) loads are independent
+        // of S^T and are issued here, before the wait for the tensor core, so their latency overlaps it.  Rows beyond Sq
+        // are clamped (their P is 0 anyway: LSE2 = +inf on padding rows).
+        uint32_t bpk[32];
+        uint32_t mb0 = 0xFFFFFFFFu, mb1 = 0xFFFFFFFFu;
+        if (has_aux) {
+          if (bbase) {
+#pragma unroll
+            for (int c = 0; c < 64; c += 2) {
+              const uint32_t lo = __ldg(bbase + (long long)min(qc0 + c, a.Sq - 1) * a.bias.sq);
+              const uint32_t hi = __ldg(bbase + (long long)min(qc0 + c + 1, a.Sq - 1) * a.bias.sq);
+              bpk[c >> 1] = lo | (hi << 16);
+            }
+          }
+          if (mbase) {
+            uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              m0 |= (__ldg(mbase + (long long)min(qc0 + c, a.Sq - 1) * a.mask.sq) != 0 ? 1u : 0u) << c;
+              m1 |= (__ldg(mbase + (long long)min(qc0 + 32 + c, a.Sq - 1) * a.mask.sq) != 0 ? 1u : 0u) << c;
+            }
+            mb0 = m0; mb1 = m1;
+          }
+        }
+        mbar_wait(&q_full[s], ph);                           // LSE2 and delta of this tile have landed (same barrier as Q_i)
+        mbar_wait(s_full, it & 1);
+        tc_fence_after();
+        TL(11);
+        float p[64];
+        {
+          uint32_t* pr = reinterpret_cast<uint32_t*>(p);
+          tmem_ld_x32(tmem_base + lane_off + TM_S + half * 64, pr);
+          tmem_ld_x32(tmem_base + lane_off + TM_S + half * 64 + 32, pr + 32);
+          tmem_wait_ld();
+        }
+        const float* lse_s = sLse + s * 128 + half * 64;
+        if (has_aux) {
+          // bias added / mask applied in the log2 domain before the exponent
 #pragma unroll
           for (int c = 0; c < 64; c += 2) {
-            const uint32_t lo = __ldg(bbase + (long long)min(qc0 + c, a.Sq - 1) * a.bias.sq);
-            const uint32_t hi = __ldg(bbase + (long long)min(qc0 + c + 1, a.Sq - 1) * a.bias.sq);
-            bpk[AUX ? (c >> 1) : 0] = lo | (hi << 16);
+            const float2 l2 = *reinterpret_cast<const float2*>(lse_s + c);
+            float b0 = alibi2 * (float)(kv_row - a.causal_off - qc0 - c) * kLn2, b1 = b0 - alibi2 * kLn2;   // ALiBi (natural-log units here)
+            if (bbase) { b0 = cvt16_to_f32<BF16>((uint16_t)(bpk[c >> 1] & 0xFFFF)); b1 = cvt16_to_f32<BF16>((uint16_t)(bpk[c >> 1] >> 16)); }
+            const float x0 = fmaf(p[c], a.scale_log2, b0 * kLog2e) - l2.x;
+            const float x1 = fmaf(p[c + 1], a.scale_log2, b1 * kLog2e) - l2.y;
+            const uint32_t mw = (c < 32) ? mb0 : mb1;
+            p[c] = ((mw >> (c & 31)) & 1u) ? ex2(x0) : 0.f;
+            p[c + 1] = ((mw >> ((c + 1) & 31)) & 1u) ? ex2(x1) : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 64; c += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(lse_s + c);
+            const float2 a01 = __ffma2_rn(make_float2(p[c], p[c + 1]), c2, make_float2(-l4.x, -l4.y));
+            const float2 a23 = __ffma2_rn(make_float2(p[c + 2], p[c + 3]), c2, make_float2(-l4.z, -l4.w));
+            p[c] = ex2(a01.x); p[c + 1] = ex2(a01.y); p[c + 2] = ex2(a23.x); p[c + 3] = ex2(a23.y);
           }
         }
-        if (mbase) {
-          uint32_t m0 = 0u, m1 = 0u;
+        const bool diag = CAUSAL && (qi0 + a.causal_off < k0 + 127);     // some (q, kv) of this tile pair lies above the diagonal
+        if (diag || kv_tail) {
+          // column c is visible to this kv row iff kv_row <= q + off  <=>  c >= kv_row - off - qc0
+          const int first_c = (diag ? max(kv_row - a.causal_off - qc0, 0) : 0) + (kv_valid ? 0 : 64);
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            m0 |= (__ldg(mbase + (long long)min(qc0 + c, a.Sq - 1) * a.mask.sq) != 0 ? 1u : 0u) << c;
-            m1 |= (__ldg(mbase + (long long)min(qc0 + 32 + c, a.Sq - 1) * a.mask.sq) != 0 ? 1u : 0u) << c;
+          for (int c = 0; c < 64; ++c) p[c] = (c >= first_c) ? p[c] : 0.f;
+        }
+        {
+          uint32_t pk[32];
+#pragma unroll
+          for (int c = 0; c < 64; c += 2) {
+            uint32_t w01 = pack2<BF16>(p[c], p[c + 1]);
+            if constexpr (DROPOUT) w01 &= keep_pair_mask((c < 32) ? keep0 : keep1, c & 31);
+            pk[c >> 1] = w01;
           }
-          mb0 = m0; mb1 = m1;
+          tmem_st_x32(tmem_base + lane_off + TM_S + half * 64, pk);   // over this thread's own S^T columns only
+          tmem_wait_st();
         }
-      }
-      if constexpr (!FOLD) mbar_wait(&q_full[s], ph);          // LSE2 and delta of this tile have landed (same barrier as Q_i)
-      mbar_wait(s_full, it & 1);
-      tc_fence_after();
-      TL(11);
-      float p[64];
-      {
-        uint32_t* pr = reinterpret_cast<uint32_t*>(p);
-        tmem_ld_x32(tmem_base + lane_off + TM_S + half * 64, pr);
-        tmem_ld_x32(tmem_base + lane_off + TM_S + half * 64 + 32, pr + 32);
-        tmem_wait_ld();
-      }
-      const float* lse_s = sLse + s * 128 + half * 64;
-      if constexpr (FOLD) {
-        // the tensor core has already subtracted LSE2 / c: P^T = 2^(c * S^T_aug)
+        tc_fence_before();
+        mbar_arrive(p_full);
+        TL(12);
+        if (it + 1 < n_iter) make_keep(qc0 + 128);            // next tile's keep bits, while dP^T is still in flight
+        // ---- dS'^T = P^T o (Z dP^T - (1-p) delta)      (dS = dS' / (1-p); the factor is folded into the dK / dQ scales)
+        mbar_wait(dp_full, it & 1);
+        tc_fence_after();
+        TL(13);
+        mbar_wait(ds_empty, (it & 1) ^ 1);  // MMAs of the previous iteration no longer read the dS^T tile
+        TL(14);
+        const float* del_s = sDelta + s * 128 + half * 64;
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-          const float2 a01 = __fmul2_rn(make_float2(p[c], p[c + 1]), c2);
-          p[c] = ex2(a01.x); p[c + 1] = ex2(a01.y);
-        }
-      } else if (has_aux) {
-        // generic path: bias added / mask applied in the log2 domain before the exponent
+        for (int g = 0; g < 2; ++g) {
+          uint32_t dpr[32];
+          tmem_ld_x32(tmem_base + lane_off + TM_DP + half * 64 + g * 32, dpr);
+          tmem_wait_ld();
+          uint32_t out[16];
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-          const float2 l2 = *reinterpret_cast<const float2*>(lse_s + c);
-          float b0 = alibi2 * (float)(kv_row - a.causal_off - qc0 - c) * kLn2, b1 = b0 - alibi2 * kLn2;   // ALiBi (natural-log units here)
-          if (bbase) { b0 = cvt16_to_f32<BF16>((uint16_t)(bpk[AUX ? (c >> 1) : 0] & 0xFFFF)); b1 = cvt16_to_f32<BF16>((uint16_t)(bpk[AUX ? (c >> 1) : 0] >> 16)); }
-          const float x0 = fmaf(p[c], a.scale_log2, b0 * kLog2e) - l2.x;
-          const float x1 = fmaf(p[c + 1], a.scale_log2, b1 * kLog2e) - l2.y;
-          const uint32_t mw = (c < 32) ? mb0 : mb1;
-          p[c] = ((mw >> (c & 31)) & 1u) ? ex2(x0) : 0.f;
-          p[c + 1] = ((mw >> ((c + 1) & 31)) & 1u) ? ex2(x1) : 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 64; c += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(lse_s + c);
-          const float2 a01 = __ffma2_rn(make_float2(p[c], p[c + 1]), c2, make_float2(-l4.x, -l4.y));
-          const float2 a23 = __ffma2_rn(make_float2(p[c + 2], p[c + 3]), c2, make_float2(-l4.z, -l4.w));
-#ifdef FASN_EXP_NO_EX2      // diagnostic build only (wrong results): how much of the step the MUFU exponentials cost
-          p[c] = a01.x; p[c + 1] = a01.y; p[c + 2] = a23.x; p[c + 3] = a23.y;
-#else
-          p[c] = ex2(a01.x); p[c + 1] = ex2(a01.y); p[c + 2] = ex2(a23.x); p[c + 3] = ex2(a23.y);
-#endif
-        }
-      }
-      const bool diag = CAUSAL && (qi0 + a.causal_off < k0 + 127);     // some (q, kv) of this tile pair lies above the diagonal
-      if (diag || kv_tail) {
-        // column c is visible to this kv row iff kv_row <= q + off  <=>  c >= kv_row - off - qc0
-        const int first_c = (diag ? max(kv_row - a.causal_off - qc0, 0) : 0) + (kv_valid ? 0 : 64);
-#pragma unroll
-        for (int c = 0; c < 64; ++c) p[c] = (c >= first_c) ? p[c] : 0.f;
-      }
-      {
-        uint32_t pk[32];
-#pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-          uint32_t w01 = pack2<BF16>(p[c], p[c + 1]);
-          // dropped entries are zeroed on the packed pair (1 PRMT + 1 AND per two elements); the 1/(1-p) factor of the
-          // kept entries is applied to dV in the epilogue
-          if constexpr (DROPOUT) w01 &= keep_pair_mask((c < 32) ? keep0 : keep1, c & 31);
-          pk[c >> 1] = w01;
-        }
-        tmem_st_x32(tmem_base + lane_off + TM_S + half * 64, pk);   // over this thread's own S^T columns only
-        tmem_wait_st();
-      }
-      tc_fence_before();
-      mbar_arrive(p_full);
-      TL(12);
-      if (it + 1 < n_iter) make_keep(qc0 + 128);            // next tile's keep bits, while dP^T is still in flight
-      // ---- dS'^T = P^T o (Z dP^T - (1-p) delta)      (dS = dS' / (1-p); the factor is folded into the dK / dQ scales)
-      mbar_wait(dp_full, it & 1);
-      tc_fence_after();
-      TL(13);
-      mbar_wait(ds_empty, (it & 1) ^ 1);  // MMAs of the previous iteration no longer read the dS^T tile
-      TL(14);
-      if constexpr (FOLD) mbar_wait(delta_full, it & 1);
-      const float* del_s = sDelta + (FOLD ? 0 : s * 128) + half * 64;
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        uint32_t dpr[32];
-        tmem_ld_x32(tmem_base + lane_off + TM_DP + half * 64 + g * 32, dpr);
-        tmem_wait_ld();
-        uint32_t out[16];
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 d4 = *reinterpret_cast<const float4*>(del_s + g * 32 + c);
-          float dp0 = __uint_as_float(dpr[c]), dp1 = __uint_as_float(dpr[c + 1]), dp2 = __uint_as_float(dpr[c + 2]), dp3 = __uint_as_float(dpr[c + 3]);
-          if constexpr (DROPOUT) {
-            const uint32_t w = (g == 0) ? keep0 : keep1;
-            dp0 = (w & (1u << (c + 0))) ? dp0 : 0.f;
-            dp1 = (w & (1u << (c + 1))) ? dp1 : 0.f;
-            dp2 = (w & (1u << (c + 2))) ? dp2 : 0.f;
-            dp3 = (w & (1u << (c + 3))) ? dp3 : 0.f;
+          for (int c = 0; c < 32; c += 4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(del_s + g * 32 + c);
+            float dp0 = __uint_as_float(dpr[c]), dp1 = __uint_as_float(dpr[c + 1]), dp2 = __uint_as_float(dpr[c + 2]), dp3 = __uint_as_float(dpr[c + 3]);
+            if constexpr (DROPOUT) {
+              const uint32_t w = (g == 0) ? keep0 : keep1;
+              dp0 = (w & (1u << (c + 0))) ? dp0 : 0.f;
+              dp1 = (w & (1u << (c + 1))) ? dp1 : 0.f;
+              dp2 = (w & (1u << (c + 2))) ? dp2 : 0.f;
+              dp3 = (w & (1u << (c + 3))) ? dp3 : 0.f;
+            }
+            const float2 e01 = __fadd2_rn(make_float2(dp0, dp1), make_float2(-d4.x, -d4.y));
+            const float2 e23 = __fadd2_rn(make_float2(dp2, dp3), make_float2(-d4.z, -d4.w));
+            const float2 s01 = __fmul2_rn(make_float2(p[g * 32 + c], p[g * 32 + c + 1]), e01);
+            const float2 s23 = __fmul2_rn(make_float2(p[g * 32 + c + 2], p[g * 32 + c + 3]), e23);
+            out[(c >> 1)] = pack2<BF16>(s01.x, s01.y);
+            out[(c >> 1) + 1] = pack2<BF16>(s23.x, s23.y);
           }
-          const float2 e01 = __fadd2_rn(make_float2(dp0, dp1), make_float2(-d4.x, -d4.y));
-          const float2 e23 = __fadd2_rn(make_float2(dp2, dp3), make_float2(-d4.z, -d4.w));
-          const float2 s01 = __fmul2_rn(make_float2(p[g * 32 + c], p[g * 32 + c + 1]), e01);
-          const float2 s23 = __fmul2_rn(make_float2(p[g * 32 + c + 2], p[g * 32 + c + 3]), e23);
-          out[(c >> 1)] = pack2<BF16>(s01.x, s01.y);
-          out[(c >> 1) + 1] = pack2<BF16>(s23.x, s23.y);
-        }
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int cc = g * 4 + q4;
-          *reinterpret_cast<uint4*>(sDS + half * BLK_BYTES + r * 128 + ((cc ^ (r & 7)) << 4)) =
-              make_uint4(out[q4 * 4], out[q4 * 4 + 1], out[q4 * 4 + 2], out[q4 * 4 + 3]);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int cc = g * 4 + q4;
+            *reinterpret_cast<uint4*>(sDS + half * BLK_BYTES + r * 128 + ((cc ^ (r & 7)) << 4)) =
+                make_uint4(out[q4 * 4], out[q4 * 4 + 1], out[q4 * 4 + 2], out[q4 * 4 + 3]);
+          }
         }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(ds_full);
+        TL(15);
       }
-      tc_fence_before();
-      fence_proxy_async_smem();
-      mbar_arrive(ds_full);
-      TL(15);
     }
 
     // ------------------------------------------------------------------ dK, dV epilogue
@@ -683,12 +720,12 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
 }  // namespace
 
-template <int D, bool BF16, bool CAUSAL, bool DROPOUT, bool AUX, bool FOLD = false>
+template <int D, bool BF16, bool CAUSAL, bool DROPOUT, bool AUX>
 static cudaError_t launch_bwd_t2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
                                 const CUtensorMap& tdk, const CUtensorMap& tdv, const CUtensorMap& tdq, const BwdArgs& a, const TensorView& dk,
                                 const TensorView& dv, cudaStream_t stream) {
-  auto kern = fasn_bwd_kernel<D, BF16, CAUSAL, DROPOUT, AUX, FOLD>;
-  constexpr int smem = FOLD ? BwdCfg<D>::SMEM_BYTES_FOLD : BwdCfg<D>::SMEM_BYTES;
+  auto kern = fasn_bwd_kernel<D, BF16, CAUSAL, DROPOUT, AUX>;
+  constexpr int smem = BwdCfg<D>::SMEM_BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   dim3 grid(((a.Skv + 127) / 128) * a.B * a.H, 1, 1);
@@ -701,11 +738,6 @@ static cudaError_t launch_bwd_t(const CUtensorMap& tq, const CUtensorMap& tk, co
                                 const CUtensorMap& tdk, const CUtensorMap& tdv, const CUtensorMap& tdq, const BwdArgs& a, const TensorView& dk,
                                 const TensorView& dv, cudaStream_t stream) {
   const bool aux = a.bias.ptr != nullptr || a.alibi != nullptr || (a.mask.ptr != nullptr && a.mask.sq != 0);
-#if FASN_BWD_FOLD_LSE
-  // the fold divides by the logit scale: positive, normal scales only
-  if (!aux && a.scale_log2 > 1e-6f && a.scale_log2 < 1e6f)
-    return launch_bwd_t2<D, BF16, CAUSAL, DROPOUT, false, true>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv, stream);
-#endif
   return aux ? launch_bwd_t2<D, BF16, CAUSAL, DROPOUT, true>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv, stream)
              : launch_bwd_t2<D, BF16, CAUSAL, DROPOUT, false>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv, stream);
 }

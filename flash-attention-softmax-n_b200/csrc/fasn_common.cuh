@@ -97,11 +97,6 @@ cudaError_t launch_bwd(int head_dim, bool bf16, bool causal, bool dropout, const
                        const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdk, const CUtensorMap& tdv,
                        const CUtensorMap& tdq_accum, const BwdArgs& a, const TensorView& dk, const TensorView& dv,
                        cudaStream_t stream);
-// paired (2-CTA) backward main kernel: head dim 128, no dense mask / bias (fasn_bwd2.cu)
-cudaError_t launch_bwd2(bool bf16, bool causal, bool dropout, const CUtensorMap& tq, const CUtensorMap& tq64, const CUtensorMap& tk,
-                        const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdo64, const CUtensorMap& tdk,
-                        const CUtensorMap& tdv, const CUtensorMap& tdq64, const BwdArgs& a, const TensorView& dk, const TensorView& dv,
-                        cudaStream_t stream);
 cudaError_t launch_bwd_finish(int head_dim, bool bf16, const TensorView& dq, const BwdArgs& a, cudaStream_t stream);
 
 // standalone softmax_n over the last axis (fasn_softmax.cu); dtype codes 0 fp16, 1 bf16, 2 fp32
@@ -111,8 +106,6 @@ cudaError_t launch_softmax_n_bwd(const void* y, const void* dy, void* dx, long l
                                  long long sdx, int dt_in, int dt_out, int vec, cudaStream_t st);
 cudaError_t launch_dropout_mask(uint8_t* out, int B, int H, int Sq, int Skv, uint32_t thr, PhiloxKey key,
                                 uint32_t bh_offset, cudaStream_t stream);
-cudaError_t launch_probe_pair(int mode, bool bf16, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& ty64,
-                              const void* x, float* c, cudaStream_t stream);
 cudaError_t launch_probe(int mode, bool bf16, const CUtensorMap& tx, const CUtensorMap& ty, const void* x, float* c,
                          cudaStream_t stream);
 

@@ -98,6 +98,15 @@ FASN_DEVICE uint32_t keep_pair_mask(uint32_t w, int pos) {
   return m;
 }
 
+// The same for keep words that were shifted so that the wanted bit is the sign bit of byte b of x_lo (low half of the
+// pair) and of x_hi (high half): the quad layout of the backward kernel, where byte b <-> kv row 8 b + lane / 4.
+FASN_DEVICE uint32_t keep_byte_pair_mask(uint32_t x_lo, uint32_t x_hi, int b) {
+  const uint32_t sel = (uint32_t)(b | 8) | ((uint32_t)(b | 8) << 4) | ((uint32_t)((4 + b) | 8) << 8) | ((uint32_t)((4 + b) | 8) << 12);
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %2, %3;\n" : "=r"(m) : "r"(x_lo), "r"(x_hi), "r"(sel));
+  return m;
+}
+
 // pack two fp32 into one 32-bit word of two 16-bit floats; `lo` lands in bits [0,16)
 template <bool BF16> FASN_DEVICE uint32_t pack2(float lo, float hi) {
   uint32_t r;
@@ -236,6 +245,17 @@ FASN_DEVICE void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+// shape 16x128b.x8 store: 16 TMEM lanes x 32 columns.  Thread t supplies, for n = 0..7,
+//   r[2n] = lane (base + t/4), column 4n + t%4        r[2n+1] = lane (base + t/4 + 8), the same column
+// which is where the packed 16-bit pairs of a 16x256b.x8 load (columns 8n + 2(t%4), +1) belong.
+FASN_DEVICE void tmem_st_16x128b_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 FASN_DEVICE void red_add_v2(float* gptr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};\n" ::"l"(gptr), "f"(a), "f"(b) : "memory");
 }
@@ -289,18 +309,6 @@ FASN_DEVICE uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint
   return d;
 }
 
-// No-swizzle ("interleaved") K-major operand: core matrix = 8 rows x 16 bytes stored contiguously (128 B); element
-// (row r, 16-byte K-chunk c) sits at  (r % 8) * 16 + (r / 8) * SBO + c * LBO.  Used by the bring-up probe for the one-K-step
-// "extension" operands of DESIGN.md section 8 (zero strides make chunks / row groups alias one another).
-FASN_DEVICE uint64_t umma_smem_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  return d;
-}
-
 // Split form for issue loops: the high word is a constant per operand kind, the low word is
 // (start address >> 4) | (LBO >> 4) << 16, so stepping through a tile is one 32-bit add of (bytes >> 4).
 __host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14) | (2u << 29); }
@@ -336,106 +344,6 @@ FASN_DEVICE void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// ------------------------------------------------------------------------------------------------
-// CTA pairs (cluster of two, tcgen05 cta_group::2).  Shared-memory addresses in the shared::cluster window are
-// (cta rank << 24) | offset; clearing bit 24 of a local address names the same offset in CTA 0 (the leader).
-// ------------------------------------------------------------------------------------------------
-FASN_DEVICE uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
-  return r;
-}
-FASN_DEVICE void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-FASN_DEVICE uint32_t mapa_shared(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
-FASN_DEVICE void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-// arrive (release at cluster scope) on an mbarrier given by its shared::cluster address (may live in the peer CTA)
-FASN_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
-}
-// The same without cluster-scope release (the form CUTLASS's ClusterBarrier uses).  A release at cluster scope costs a
-// cluster-level memory barrier per arrive (~1000+ cycles under load, measured in the paired backward); when everything
-// the arrive publishes is ordered by tcgen05 fences / proxy fences into the CTA's own memories, CTA scope is enough.
-FASN_DEVICE void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
-}
-FASN_DEVICE bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
-      : "memory");
-  return ok != 0;
-}
-// wait on a local mbarrier whose arrivals may come from the peer CTA (acquire at cluster scope)
-FASN_DEVICE void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-#ifndef FASN_NO_WATCHDOG
-  uint32_t spins = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > FASN_WATCHDOG_POLLS) { __trap(); }
-  }
-#else
-  while (!mbar_try_wait_cluster(bar, parity)) {}
-#endif
-}
-FASN_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
-
-// 4-D tiled load into THIS CTA's shared memory whose completion bytes are counted on the LEADER CTA's mbarrier
-// (same offset in CTA 0): both CTAs of a pair feed one barrier that the single MMA-issuing thread waits on.
-FASN_DEVICE void tma_load_4d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
-          "r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-
-template <uint32_t COLS> FASN_DEVICE void tmem_alloc_pair(uint32_t* smem_result) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_result)), "n"(COLS)
-               : "memory");
-}
-FASN_DEVICE void tmem_relinquish_pair() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory"); }
-template <uint32_t COLS> FASN_DEVICE void tmem_dealloc_pair(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(COLS) : "memory");
-}
-// All previously issued cta_group::2 MMAs of this thread arrive (once) on the mbarrier at this offset in BOTH CTAs.
-FASN_DEVICE void tc_commit_pair(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
-               : "memory");
-}
-// cta_group::2 MMAs: D rows [0,128) live in CTA 0's TMEM, [128,256) in CTA 1's (M = 256); with M = 128 each CTA holds
-// 64 rows, columns [0,N/2) on lanes 0-63 and [N/2,N) on lanes 64-127.  A comes from each CTA's own smem / TMEM,
-// B is split along N: each CTA supplies N/2 rows from the same shared-memory offset.
-FASN_DEVICE void umma2_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-FASN_DEVICE void umma2_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }

@@ -51,7 +51,7 @@ class FasnParams(ctypes.Structure):
 
 EXPORTS = ("fasn_version", "fasn_last_error", "fasn_fwd", "fasn_bwd", "fasn_bwd_workspace",
            "fasn_dropout_mask", "fasn_probe", "fasn_attention_host", "fasn_profile", "fasn_profile_read",
-           "fasn_set_bwd_impl", "fasn_softmax_n_fwd", "fasn_softmax_n_bwd")
+           "fasn_softmax_n_fwd", "fasn_softmax_n_bwd")
 
 _lib: Optional[ctypes.CDLL] = None
 _lock = threading.Lock()
@@ -109,8 +109,6 @@ def load() -> ctypes.CDLL:
                                            ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint32,
                                            ctypes.c_void_p]
         lib.fasn_softmax_n_bwd.restype = ctypes.c_int
-        lib.fasn_set_bwd_impl.argtypes = [ctypes.c_int]
-        lib.fasn_set_bwd_impl.restype = ctypes.c_int
         lib.fasn_profile.argtypes = [ctypes.c_int]
         lib.fasn_profile.restype = ctypes.c_int
         lib.fasn_profile_read.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32),

@@ -210,6 +210,10 @@ def flash_attention_n(
     Dp = min(d for d in _SUPPORTED_HEAD_DIMS if d >= max(E, Ev))
     if not 0.0 <= dropout_p < 1.0:
         raise ValueError("dropout_p must be in [0, 1)")
+    if dropout_p > 0.0 and round((1.0 - dropout_p) * 256.0) < 1:
+        # the counter-based generator decides with 8-bit uniforms: P(keep) = round(256 (1-p)) / 256, kept entries are
+        # scaled by its inverse; a keep probability that rounds to 0 has no unbiased estimator
+        raise ValueError(f"dropout_p={dropout_p} is closer to 1 than the dropout generator resolves (1/256)")
     sm_scale = 1.0 / sqrt(E) if scale is None else float(scale)           # flash_attn.py:59, 81-83
 
     if E != Dp:

@@ -21,7 +21,8 @@
  *   - every function returns 0 on success, a negative FASN_E* code for a rejected argument, or a positive
  *     cudaError_t; fasn_last_error() returns a thread-local description of the last failure;
  *   - launches are asynchronous on `stream`; nothing here synchronises the device;
- *   - re-entrant; the only global state is an immutable driver entry point looked up once.
+ *   - re-entrant.  Process-wide state, all mutex-guarded: the driver entry point looked up once (immutable), the
+ *     fasn_profile event lists, and the device arena of fasn_attention_host (one per device, grown on demand).
  */
 #ifndef FASN_H_
 #define FASN_H_
@@ -117,11 +118,6 @@ int fasn_bwd_workspace(const FasnParams* p, uint64_t* delta_bytes, uint64_t* dq_
  * the caller must have synchronised the stream(s) first. */
 int fasn_profile(int enable);
 
-/* Backward main-kernel selection (process-wide): 0 = automatic (whichever is faster for the shape), 1 = the single-CTA
- * kernel (csrc/fasn_bwd.cu), 2 = the CTA-pair kernel (csrc/fasn_bwd2.cu) wherever it applies (head dim 128 without dense
- * mask / bias; other shapes still take the single-CTA kernel).  The environment variable FASN_BWD_IMPL sets the
- * initial value.  Returns the previous setting, or FASN_EINVAL. */
-int fasn_set_bwd_impl(int impl);
 int fasn_profile_read(double* fwd_ms, int32_t* fwd_launches, double* bwd_ms, int32_t* bwd_launches);
 
 /* Test hook: write the dropout keep mask the kernels use, as (B,H,L,S) uint8 (1 = keep), to `out`. */
@@ -134,14 +130,9 @@ int fasn_dropout_mask(uint8_t* out, int32_t batch, int32_t heads, int32_t seqlen
  *   mode 1: C = X * Y    (A from tensor memory, B MN-major)      -- the P V form
  *   mode 2: C = X^T * Y  (A, B MN-major in shared memory)        -- the dQ = dS K form
  *   mode 3: C = X * Y    (A K-major, B MN-major in shared memory)-- the dK = dS^T Q form
- *   modes 4-6 (building block of the LSE2 fold): mode 0 plus a ninth K-step whose operands are no-swizzle K-major
- *           "extension" tiles -- C = X * Y^T + e_j (4) or + 2 e_j (5: second K-chunk aliases the first, LBO = 0;
- *           6: additionally one core matrix serves every row group of the A side, SBO = 0), e_j = 3.25 * x[j][0].
- * x, y: 128x128 row-major 16-bit device arrays; c: 128x128 row-major fp32.
- * CTA-pair forms (cluster of two CTAs, tcgen05 cta_group::2; the paired backward kernel):
- *   mode 10: C[256x128] = X[256x128] * Y[128x128]^T   (M = 256, B split along N between the two CTAs)
- *   mode 11: C[128x128] = X[256x128]^T * Y[256x128]   (M = 128, K = 256, A written by local + remote stores)
- *   mode 12: C[256x128] = X[256x128] * Y[128x128]     (M = 256, A in tensor memory) */
+ *   mode 4: mode 1 with A staged the way the backward kernel's compute warps do it: read from tensor memory as fp32 with
+ *           tcgen05.ld.16x256b, packed to 16-bit pairs, stored with tcgen05.st.16x128b.
+ * x, y: 128x128 row-major 16-bit device arrays; c: 128x128 row-major fp32. */
 int fasn_probe(int mode, uint32_t dtype, const void* x, const void* y, float* c, void* stream);
 
 /* Standalone fused softmax_n over the last (contiguous) axis: y_i = exp(x_i) / (n + sum_j exp(x_j)) for `rows` rows of

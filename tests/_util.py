@@ -34,6 +34,7 @@ def oracle_all(q, k, v, do, **kw):
 def native_lowp_all(q, k, v, do, **kw):
     """The same oracle evaluated natively in the inputs' low-precision dtype on the GPU: the error level the
     reference's own eager path has (used to scale the max-abs criterion)."""
+    kw = {a: (b.to(q.device) if torch.is_tensor(b) else b) for a, b in kw.items()}
     return orc.attention_fwd_bwd(q, k, v, do, dtype=q.dtype, **kw)
 
 

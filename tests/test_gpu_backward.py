@@ -19,6 +19,11 @@ CASES = [
     (6, 1, 1024, 1024, 64, 1.0, True, 0.5),      # the reference's GPU test shape (tests/gpu/core/test_flash_attn.py:16-18)
     (5, 8, 256, 384, 128, 0.5, True, None),      # 40 units: both halves of the launch order (unit-major head, tile-major tail of 32)
     (7, 6, 200, 200, 64, 1.0, True, None),       # 42 units, ragged
+    (1, 2, 256, 333, 128, 0.5, False, None),     # three K/V tiles, ragged tail
+    (1, 2, 333, 200, 128, 1.0, True, None),      # S < L causal at head dim 128
+    (2, 1, 96, 160, 128, 0.5, True, None),       # S > L causal
+    (1, 2, 1024, 1024, 128, 0.5, True, None),    # 8 x 8 tiles, causal trip counts
+    (1, 1, 512, 768, 128, 0.0, False, 0.2),
 ]
 
 
@@ -33,55 +38,6 @@ def test_backward_matches_oracle(fasn_lib, B, H, L, S, D, n, causal, scale, dtyp
     for name, g, w, nat in zip(("O", "dQ", "dK", "dV"), got, want, native):
         assert g.shape == w.shape and g.dtype == dtype
         check_close(name, g, w, nat, dtype, rel_scale=1.5)
-
-
-PAIR_CASES = [   # head dim 128 without mask / bias runs the CTA-pair kernel (csrc/fasn_bwd2.cu): two K/V tiles per cluster
-    (1, 1, 128, 128, 128, 1.0, False, None),     # one K/V tile: the second CTA of the pair owns no keys
-    (1, 2, 256, 333, 128, 0.5, False, None),     # three K/V tiles, ragged tail
-    (1, 2, 333, 200, 128, 1.0, True, None),      # S < L causal: rows that see no key
-    (2, 1, 96, 160, 128, 0.5, True, None),       # S > L causal
-    (1, 2, 1024, 1024, 128, 0.5, True, None),    # 8 x 8 tiles, causal trip counts per pair
-    (1, 1, 512, 768, 128, 0.0, False, 0.2),
-]
-
-
-@pytest.fixture
-def pair_bwd(fasn_lib):
-    prev = fasn_lib.fasn_set_bwd_impl(2)
-    yield
-    fasn_lib.fasn_set_bwd_impl(prev)
-
-
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("B,H,L,S,D,n,causal,scale", PAIR_CASES + [c for c in CASES if c[4] == 128])
-def test_backward_pair_kernel_matches_oracle(fasn_lib, pair_bwd, B, H, L, S, D, n, causal, scale, dtype):
-    test_backward_matches_oracle(fasn_lib, B, H, L, S, D, n, causal, scale, dtype)
-
-
-@pytest.fixture
-def single_cta_bwd(fasn_lib):
-    prev = fasn_lib.fasn_set_bwd_impl(1)
-    yield
-    fasn_lib.fasn_set_bwd_impl(prev)
-
-
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("B,H,L,S,D,n,causal,scale", [c for c in CASES + PAIR_CASES[1:5] if c[4] == 128])
-def test_backward_single_cta_kernel_d128(fasn_lib, single_cta_bwd, B, H, L, S, D, n, causal, scale, dtype):
-    """The single-CTA kernel stays the path for masks / bias / head dim 64; keep its head-dim-128 instance covered too."""
-    test_backward_matches_oracle(fasn_lib, B, H, L, S, D, n, causal, scale, dtype)
-
-
-@pytest.mark.parametrize("dtype", [torch.float16])
-@pytest.mark.parametrize("causal", [False, True])
-def test_backward_dropout_same_mask_single_cta(fasn_lib, single_cta_bwd, dtype, causal):
-    test_backward_dropout_same_mask(fasn_lib, dtype, causal)
-
-
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("causal", [False, True])
-def test_backward_dropout_same_mask_pair(fasn_lib, pair_bwd, dtype, causal):
-    test_backward_dropout_same_mask(fasn_lib, dtype, causal)
 
 
 @pytest.mark.parametrize("name", ["c1", "causal", "n0c"])
