@@ -153,6 +153,35 @@ struct ScopedEvents {
   }
 };
 
+// Work counters of the persistent kernels: a pool of (next item, CTAs finished) pairs per device, handed out round-robin,
+// one pair per launch.  Every kernel leaves its pair at zero (the last CTA to finish resets it), so a pair is ready again
+// long before its turn comes round: a collision would need kSchedSlots launches in flight at once.
+constexpr int kSchedSlots = 4096;
+struct DeviceState {
+  int* sched = nullptr;
+  int num_sms = 0;
+  unsigned next = 0;
+};
+std::mutex g_dev_mu;
+std::map<int, DeviceState> g_dev;
+
+// (counter pair for one launch, SM count) of the device that is current (the DeviceGuard has bound the tensors' device)
+int sched_slot(int** slot, int* num_sms) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail_cuda(e, "cudaGetDevice");
+  std::lock_guard<std::mutex> l(g_dev_mu);
+  DeviceState& d = g_dev[dev];
+  if (d.sched == nullptr) {
+    if ((e = cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return fail_cuda(e, "cudaDeviceGetAttribute");
+    if ((e = cudaMalloc(&d.sched, 2 * kSchedSlots * sizeof(int))) != cudaSuccess) return fail_cuda(e, "scheduler counters cudaMalloc");
+    if ((e = cudaMemset(d.sched, 0, 2 * kSchedSlots * sizeof(int))) != cudaSuccess) return fail_cuda(e, "scheduler counters cudaMemset");
+  }
+  *slot = d.sched + 2 * (d.next++ % kSchedSlots);
+  *num_sms = d.num_sms;
+  return 0;
+}
+
 fasn::AuxView aux_view(const FasnAux& a) { return fasn::AuxView{a.ptr, a.stride_b, a.stride_h, a.stride_q}; }
 fasn::TensorView tensor_view(const FasnTensor& t) { return fasn::TensorView{t.ptr, t.stride_b, t.stride_h, t.stride_s}; }
 
@@ -216,6 +245,12 @@ int fasn_fwd(const FasnParams* p) {
   a.key = fasn::make_philox_key(p->philox_seed, p->philox_offset, a.drop_thr);
   a.bh_offset = (uint32_t)p->bh_offset;
   a.sched_group = fasn::sched_group_size(2ll * D * (2ll * L + 2ll * S));            // Q, O, K, V of one unit
+  {
+    int num_sms = 0;
+    if (int rc = sched_slot(&a.sched, &num_sms)) return rc;
+    const long long items = (long long)B * H * ((L + 255) / 256);
+    a.grid_ctas = (int)(items < num_sms ? items : num_sms);
+  }
 #ifdef FASN_TIMELINE
   {
     extern unsigned long long* g_fasn_timeline_fwd; extern unsigned int g_fasn_timeline_fwd_xy[2];

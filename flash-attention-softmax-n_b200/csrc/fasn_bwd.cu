@@ -40,21 +40,40 @@ namespace {
 #define TL_DECL(role) unsigned long long* tl_p = (a.dbg && kt == (int)a.dbg_x && bh == (int)a.dbg_y) ? a.dbg + (role) * 2048 : nullptr; int tl_i = 0;
 #define TL_ONLY(cond) do { if (!(cond)) tl_p = nullptr; } while (0)
 #define TL(tag) do { if (tl_p && tl_i < 2048) tl_p[tl_i++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
+// Per-CTA record (every CTA, thread 0): [4 b] = globaltimer at entry, [4 b + 1] = at exit, [4 b + 2] = clock64 cycles in
+// between, [4 b + 3] = (smid << 32) | iterations, stored behind the five role timelines.  scripts/cta_profile.py fits
+// lifetime = overhead + period * iterations and adds up the per-SM busy time.
+#define TL_CTA_BEGIN() unsigned long long cta_g0 = 0, cta_c0 = 0; if (a.dbg && threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(cta_g0)); cta_c0 = clock64(); }
+#define TL_CTA_END(iters) do { if (a.dbg && threadIdx.x == 0) { unsigned long long g1; unsigned int sm; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1)); asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); \
+    unsigned long long* rec = a.dbg + 5 * 2048 + 4ull * blockIdx.x; rec[0] = cta_g0; rec[1] = g1; rec[2] = clock64() - cta_c0; rec[3] = ((unsigned long long)sm << 32) | (unsigned int)(iters); } } while (0)
 #else
 #define TL_DECL(role)
 #define TL_ONLY(cond)
 #define TL(tag)
+#define TL_CTA_BEGIN()
+#define TL_CTA_END(iters)
 #endif
 
 
 constexpr int kBwdThreads = 512;
+// dS^T is handed to the tensor pipe in two halves (kv rows [0,16) / [16,32) of every 32-row group = even / odd K-steps of
+// dQ = dS K), so the first half of the dQ MMA runs while the compute warps still produce the second half.
+#ifndef FASN_BWD_SPLIT_DS
+#define FASN_BWD_SPLIT_DS 0
+#endif
+// Register budgets after the role split (setmaxnreg): 8 compute warps, 4 dQ reducer warps (the whole fp32 dQ tile row of a
+// thread, D values, lives in registers), 4 producer / MMA / idle warps.  256 x 152 + 128 x 152 + 128 x 56 = 65536 at D = 128,
+// 256 x 176 + 128 x 104 + 128 x 56 = 65536 at D = 64.
+template <int D> struct BwdRegs {
+  static constexpr int kCompute = (D == 128) ? 152 : 176, kReduce = (D == 128) ? 152 : 104, kOther = 56;
+};
 
 template <int D> struct BwdCfg {
   static constexpr int DB = D / 64;
   static constexpr int TILE_BYTES = 128 * D * 2;
   static constexpr int BLK_BYTES = 128 * 128;
   static constexpr int DS_BYTES = 2 * BLK_BYTES;                  // dS^T: [2 q-blocks][128 kv rows][128 B]
-  static constexpr int NUM_BARS = 18;
+  static constexpr int NUM_BARS = 19;
   static constexpr int DQ_STAGE_BYTES = 128 * 32 * 4;             // dQ staging chunk: 128 rows x 32 fp32 columns
   // K, V, Q ring (2), dO (1), dS^T, dQ staging (2 chunks), LSE2 ring + delta ring (2 x 2 x 512 B), barriers, tmem slot
   static constexpr int SMEM_BYTES = 5 * TILE_BYTES + DS_BYTES + 2 * DQ_STAGE_BYTES + 4 * 512 + NUM_BARS * 8 + 16;
@@ -90,6 +109,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   constexpr int DB = Cfg::DB, TILE_BYTES = Cfg::TILE_BYTES, BLK_BYTES = Cfg::BLK_BYTES;
   constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DQ = 128, TM_DV = 256, TM_DK = 256 + D;
 
+  TL_CTA_BEGIN();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const TileCoord tcd = decode_block(blockIdx.x, (a.Skv + 127) >> 7, a.B * a.H, a.sched_group);
@@ -146,6 +166,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* dq_full = bars + 14;
   uint64_t* dq_empty = bars + 15;  // 128 arrivals
   uint64_t* dkv_full = bars + 16;
+  uint64_t* ds_half = bars + 18;   // 256 arrivals: kv rows [0,16) of every 32-row group of dS^T are in shared memory
   uint64_t* dv_full = bars + 17;   // the last dV MMA has completed: the dV epilogue overlaps the last dQ / dK MMAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NUM_BARS);
 
@@ -159,7 +180,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     mbar_init(do_full, 1); mbar_init(do_empty, 1);
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(ds_empty, 1);
-    mbar_init(dq_full, 1); mbar_init(dq_empty, 128); mbar_init(dkv_full, 1); mbar_init(dv_full, 1);
+    mbar_init(dq_full, 1); mbar_init(dq_empty, 128); mbar_init(dkv_full, 1); mbar_init(dv_full, 1); mbar_init(ds_half, 256);
     fence_mbar_init();
     fence_proxy_async_smem();
     mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
@@ -185,7 +206,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 12) {
-    setmaxnreg_dec<56>();
+    setmaxnreg_dec<BwdRegs<D>::kOther>();
     if (warp == 12 && lane == 0) {
       // ---------------------------------------------------------------- TMA producer
       const float* lse2 = lse2_ws;
@@ -215,12 +236,14 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       constexpr uint32_t hi_desc = umma_desc_hi(1024);
       constexpr uint32_t TILE16 = TILE_BYTES >> 4;
       const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
-      // K-major views (LBO unused) and MN-major views (LBO = next 64-wide block) of the operand tiles
-      const uint32_t k_km = umma_desc_lo(smem_u32(sK), 16), v_km = umma_desc_lo(smem_u32(sV), 16);
-      const uint32_t q_km = umma_desc_lo(smem_u32(sQ), 16), do_km = umma_desc_lo(smem_u32(sDO), 16);
-      const uint32_t ds_km = umma_desc_lo(smem_u32(sDS), 16);
-      const uint32_t k_mn = umma_desc_lo(smem_u32(sK), BLK_BYTES), q_mn = umma_desc_lo(smem_u32(sQ), BLK_BYTES);
-      const uint32_t do_mn = umma_desc_lo(smem_u32(sDO), BLK_BYTES), ds_mn = umma_desc_lo(smem_u32(sDS), BLK_BYTES);
+      // Descriptor low words = (shared-memory address >> 4) | (LBO >> 4) << 16.  Every operand tile sits at a compile-time
+      // offset from the CTA's shared-memory base, so one register plus immediates describes them all; the base is made
+      // opaque once per Q tile (asm below) so that the compiler recomputes base + immediate next to each MMA instead of
+      // hoisting ~60 loop-invariant descriptor words into registers it does not have (this warp runs on 56 registers).
+      //   K-major views: LBO unused (1);  MN-major views: LBO = next 64-wide block
+      constexpr uint32_t KM = 1u << 16, MN = static_cast<uint32_t>(BLK_BYTES >> 4) << 16;
+      constexpr uint32_t oK = 0, oV = TILE16, oQ = 2 * TILE16, oDO = 4 * TILE16, oDS = 5 * TILE16;
+      uint32_t sb = (smem_u32(smem) & 0x3FFFF) >> 4;
       auto issue_kmajor = [&](uint32_t tm_dst, uint32_t a_lo, uint32_t b_lo) {  // D[128x128] = A B^T over K = head dim
 #pragma unroll
         for (int kb = 0; kb < D / 16; ++kb) {
@@ -235,15 +258,16 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_after();
       TL(1);
       if (elect_one()) {
-        issue_kmajor(TM_S, k_km, q_km);
+        issue_kmajor(TM_S, sb + oK + KM, sb + oQ + KM);
         tc_commit(s_full);
       }
       __syncwarp();
       mbar_wait(do_full, 0);
       tc_fence_after();
-      if (elect_one()) { issue_kmajor(TM_DP, v_km, do_km); tc_commit(dp_full); }
+      if (elect_one()) { issue_kmajor(TM_DP, sb + oV + KM, sb + oDO + KM); tc_commit(dp_full); }
       __syncwarp();
       for (int it = 0; it < n_iter; ++it) {
+        asm volatile("" : "+r"(sb));
         const int s = it & 1;
         const int s1 = s ^ 1;
         const uint32_t ph1 = ((it + 1) >> 1) & 1;
@@ -255,7 +279,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (elect_one()) {
 #pragma unroll
           for (int kb = 0; kb < 8; ++kb)
-            umma_ts(tm + TM_DV, tm + TM_S + (kb >> 2) * 64 + (kb & 3) * 8, umma_desc_join(do_mn + kb * (2048 >> 4), hi_desc),
+            umma_ts(tm + TM_DV, tm + TM_S + (kb >> 2) * 64 + (kb & 3) * 8, umma_desc_join(sb + oDO + MN + kb * (2048 >> 4), hi_desc),
                     idesc_dv, (it > 0 || kb > 0) ? 1u : 0u);
           tc_commit(do_empty);         // dO_i is dead once dP^T_i (issued earlier) and dV_i have completed
           if (!more) tc_commit(dv_full);
@@ -267,25 +291,36 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tc_fence_after();
           TL(3);
           if (elect_one()) {
-            issue_kmajor(TM_S, k_km, q_km + s1 * TILE16);
+            issue_kmajor(TM_S, sb + oK + KM, sb + oQ + KM + s1 * TILE16);
             tc_commit(s_full);
           }
           __syncwarp();
         }
         // dQ_i = dS K first (its consumers, the reducer warps, then drain TMEM while dK executes) ;  dK += dS^T Q_i
+#if FASN_BWD_SPLIT_DS
+        mbar_wait(ds_half, it & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int kb = 0; kb < 8; kb += 2)
+            umma_ss(tm + TM_DQ, umma_desc_join(sb + oDS + MN + kb * (2048 >> 4), hi_desc), umma_desc_join(sb + oK + MN + kb * (2048 >> 4), hi_desc),
+                    idesc_dq, kb > 0 ? 1u : 0u);
+        }
+        __syncwarp();
+#endif
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
         TL(4);
         if (elect_one()) {
 #pragma unroll
-          for (int kb = 0; kb < 8; ++kb)
-            umma_ss(tm + TM_DQ, umma_desc_join(ds_mn + kb * (2048 >> 4), hi_desc), umma_desc_join(k_mn + kb * (2048 >> 4), hi_desc),
+          for (int kb = FASN_BWD_SPLIT_DS ? 1 : 0; kb < 8; kb += FASN_BWD_SPLIT_DS ? 2 : 1)
+            umma_ss(tm + TM_DQ, umma_desc_join(sb + oDS + MN + kb * (2048 >> 4), hi_desc), umma_desc_join(sb + oK + MN + kb * (2048 >> 4), hi_desc),
                     idesc_dq, kb > 0 ? 1u : 0u);
           tc_commit(dq_full);
 #pragma unroll
           for (int kb = 0; kb < 8; ++kb) {
             const uint32_t off = ((kb >> 2) * BLK_BYTES + (kb & 3) * 32) >> 4;
-            umma_ss(tm + TM_DK, umma_desc_join(ds_km + off, hi_desc), umma_desc_join(q_mn + s * TILE16 + kb * (2048 >> 4), hi_desc),
+            umma_ss(tm + TM_DK, umma_desc_join(sb + oDS + KM + off, hi_desc), umma_desc_join(sb + oQ + MN + s * TILE16 + kb * (2048 >> 4), hi_desc),
                     idesc_dk, (it > 0 || kb > 0) ? 1u : 0u);
           }
           tc_commit(&q_empty[s]);      // Q_i, LSE2_i and delta_i stay valid until the compute warps are done with tile i
@@ -300,7 +335,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(dq_empty, it & 1);
           tc_fence_after();
           TL(6);
-          if (elect_one()) { issue_kmajor(TM_DP, v_km, do_km); tc_commit(dp_full); }
+          if (elect_one()) { issue_kmajor(TM_DP, sb + oV + KM, sb + oDO + KM); tc_commit(dp_full); }
           __syncwarp();
         }
       }
@@ -311,10 +346,15 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // ------------------------------------------------------------------ dQ reducers
     // TMEM -> registers -> swizzled fp32 staging chunk in smem -> TMA reduce-add into dq_accum (the L2 does the adds
     // a full 128-byte line at a time; per-thread red.global instructions are an order of magnitude slower here).
-    setmaxnreg_dec<104>();
+    // The whole dQ tile is pulled into registers first and its tensor-memory columns are released at once: dP^T of the next
+    // Q tile reuses them, and the chain dS -> dQ MMA -> drain -> dP^T MMA -> dS is the critical path of an iteration (the
+    // staging stores below compete for the shared-memory port with the tensor core's operand reads and take ~1000 cycles).
+    if constexpr (BwdRegs<D>::kReduce > 128) setmaxnreg_inc<BwdRegs<D>::kReduce>(); else setmaxnreg_dec<BwdRegs<D>::kReduce>();
     const int r = (warp & 3) * 32 + lane;                 // query row inside the tile
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     constexpr int NCH = D / 32;                           // 32-column chunks per dQ tile
+    uint8_t* const stage_row = sDQ + r * 128;
+    const int rx = (r & 7) << 4;
     TL_DECL(3)
     TL_ONLY(threadIdx.x == 256);
     for (int it = 0; it < n_iter; ++it) {
@@ -322,21 +362,23 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
       TL(30);
+      uint32_t v[D];
+#pragma unroll
+      for (int cb = 0; cb < NCH; ++cb) tmem_ld_x32(tmem_base + lane_off + TM_DQ + cb * 32, v + cb * 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(dq_empty);                                // the dQ columns may be overwritten by dP^T now
+      TL(31);
 #pragma unroll
       for (int hb = 0; hb < NCH / 2; ++hb) {                // 64 columns (both staging chunks) per round
-        uint32_t v[64];
-        tmem_ld_x32(tmem_base + lane_off + TM_DQ + hb * 64, v);
-        tmem_ld_x32(tmem_base + lane_off + TM_DQ + hb * 64 + 32, v + 32);
-        tmem_wait_ld();
-        if (hb == NCH / 2 - 1) { tc_fence_before(); mbar_arrive(dq_empty); TL(31); }   // dQ columns may be overwritten by dP^T now
         if (threadIdx.x == 256) tma_store_wait_read<0>();   // the previous round's reduces have read both staging chunks
         named_bar_sync(2, 128);
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
           for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<uint4*>(sDQ + ch * Cfg::DQ_STAGE_BYTES + r * 128 + ((g ^ (r & 7)) << 4)) =
-                make_uint4(v[ch * 32 + g * 4], v[ch * 32 + g * 4 + 1], v[ch * 32 + g * 4 + 2], v[ch * 32 + g * 4 + 3]);
+            *reinterpret_cast<uint4*>(stage_row + ch * Cfg::DQ_STAGE_BYTES + ((g << 4) ^ rx)) =
+                make_uint4(v[hb * 64 + ch * 32 + g * 4], v[hb * 64 + ch * 32 + g * 4 + 1], v[hb * 64 + ch * 32 + g * 4 + 2], v[hb * 64 + ch * 32 + g * 4 + 3]);
         fence_proxy_async_smem();
         named_bar_sync(3, 128);
         if (threadIdx.x == 256) {
@@ -346,10 +388,10 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
-    if (threadIdx.x == 256) tma_store_wait_all();
+    if (threadIdx.x == 256) tma_store_wait_read<0>();   // the staging chunks have been read; the L2 adds complete on their own before the grid ends
   } else {
     // -------------------------------------------------------------------- compute warps
-    setmaxnreg_inc<176>();
+    setmaxnreg_inc<BwdRegs<D>::kCompute>();
     const int quarter = warp & 3;
     const int half = warp >> 2;
     const int r = quarter * 32 + lane;                     // kv row inside the tile (row layout: AUX loop, epilogue)
@@ -503,6 +545,9 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               *reinterpret_cast<uint32_t*>(ds_base + j * (8 * 128) + choff) = pack2<BF16>(s01.x, s01.y);
             }
           }
+#if FASN_BWD_SPLIT_DS
+          if (h16 == 0) { fence_proxy_async_smem(); mbar_arrive(ds_half); }
+#endif
         }
         tc_fence_before();
         fence_proxy_async_smem();
@@ -662,6 +707,9 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         tc_fence_before();
         fence_proxy_async_smem();
+#if FASN_BWD_SPLIT_DS
+        mbar_arrive(ds_half);
+#endif
         mbar_arrive(ds_full);
         TL(15);
       }
@@ -716,6 +764,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 14) tmem_dealloc<512>(tmem_base);
+  TL_CTA_END(n_iter);
 }
 
 }  // namespace

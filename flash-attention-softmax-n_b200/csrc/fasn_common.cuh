@@ -34,6 +34,9 @@ struct FwdArgs {
   PhiloxKey key;
   uint32_t bh_offset;
   int sched_group;        // units scheduled tile-major at the end of the launch (decode_block)
+  int* sched;             // persistent kernels: [0] next work item (beyond the first wave), [1] CTAs finished; both zero before
+                          // and after every launch (the last CTA to finish resets them)
+  int grid_ctas;          // CTAs to launch: min(SMs of the device, work items)
   unsigned long long* dbg;   // FASN_TIMELINE builds only
   unsigned int dbg_x, dbg_y;
 };
