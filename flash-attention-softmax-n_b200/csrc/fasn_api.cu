@@ -7,6 +7,8 @@
 #include <initializer_list>
 #include <map>
 #include <mutex>
+#include <set>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -420,6 +422,54 @@ int fasn_probe(int mode, uint32_t dtype, const void* x, const void* y, float* c,
   if (int rc = make_map(&ty, y, 0, 0, 128, 1, 1, 128, 128, bf16, "y")) return rc;
   cudaError_t e = fasn::launch_probe(mode, bf16, tx, ty, x, c, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda(e, "fasn_probe launch");
+  return 0;
+}
+
+namespace {
+std::mutex g_peer_mu;
+std::set<std::pair<int, int>> g_peer_enabled;     // (accessing device, accessed device) pairs already enabled in this process
+
+// Device that owns `p`, or -1 for host memory / unknown pointers.
+int device_of(const void* p) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? at.device : -1;
+}
+
+// Without peer access enabled between the two devices IN THIS PROCESS the runtime stages a device-to-device copy through
+// host memory (measured 30 GB/s instead of 790 GB/s over NVLink), also for memory mapped with cudaIpcOpenMemHandle.
+cudaError_t ensure_peer_access(int from, int to) {
+  if (from < 0 || to < 0 || from == to) return cudaSuccess;
+  std::lock_guard<std::mutex> l(g_peer_mu);
+  if (g_peer_enabled.count({from, to})) return cudaSuccess;
+  int can = 0;
+  cudaError_t e = cudaDeviceCanAccessPeer(&can, from, to);
+  if (e != cudaSuccess) return e;
+  if (can) {
+    int prev = -1;
+    if ((e = cudaGetDevice(&prev)) != cudaSuccess) return e;
+    if ((e = cudaSetDevice(from)) != cudaSuccess) return e;
+    e = cudaDeviceEnablePeerAccess(to, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) return e;
+  }
+  g_peer_enabled.insert({from, to});
+  return cudaSuccess;
+}
+}  // namespace
+
+int fasn_copy_async(void* dst, const void* src, uint64_t bytes, void* stream) {
+  if (dst == nullptr || src == nullptr) return fail(FASN_EINVAL, "fasn_copy_async: null pointer");
+  if (bytes == 0) return 0;
+  {
+    const int ds = device_of(src), dd = device_of(dst);
+    cudaError_t pe = ensure_peer_access(ds, dd);
+    if (pe == cudaSuccess) pe = ensure_peer_access(dd, ds);
+    if (pe != cudaSuccess) return fail_cuda(pe, "fasn_copy_async: enabling peer access");
+  }
+  cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda(e, "fasn_copy_async");
   return 0;
 }
 

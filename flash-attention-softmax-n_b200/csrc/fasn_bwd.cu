@@ -56,11 +56,6 @@ namespace {
 
 
 constexpr int kBwdThreads = 512;
-// dS^T is handed to the tensor pipe in two halves (kv rows [0,16) / [16,32) of every 32-row group = even / odd K-steps of
-// dQ = dS K), so the first half of the dQ MMA runs while the compute warps still produce the second half.
-#ifndef FASN_BWD_SPLIT_DS
-#define FASN_BWD_SPLIT_DS 0
-#endif
 // Register budgets after the role split (setmaxnreg): 8 compute warps, 4 dQ reducer warps (the whole fp32 dQ tile row of a
 // thread, D values, lives in registers), 4 producer / MMA / idle warps.  256 x 152 + 128 x 152 + 128 x 56 = 65536 at D = 128,
 // 256 x 176 + 128 x 104 + 128 x 56 = 65536 at D = 64.
@@ -73,7 +68,7 @@ template <int D> struct BwdCfg {
   static constexpr int TILE_BYTES = 128 * D * 2;
   static constexpr int BLK_BYTES = 128 * 128;
   static constexpr int DS_BYTES = 2 * BLK_BYTES;                  // dS^T: [2 q-blocks][128 kv rows][128 B]
-  static constexpr int NUM_BARS = 19;
+  static constexpr int NUM_BARS = 18;
   static constexpr int DQ_STAGE_BYTES = 128 * 32 * 4;             // dQ staging chunk: 128 rows x 32 fp32 columns
   // K, V, Q ring (2), dO (1), dS^T, dQ staging (2 chunks), LSE2 ring + delta ring (2 x 2 x 512 B), barriers, tmem slot
   static constexpr int SMEM_BYTES = 5 * TILE_BYTES + DS_BYTES + 2 * DQ_STAGE_BYTES + 4 * 512 + NUM_BARS * 8 + 16;
@@ -166,7 +161,6 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* dq_full = bars + 14;
   uint64_t* dq_empty = bars + 15;  // 128 arrivals
   uint64_t* dkv_full = bars + 16;
-  uint64_t* ds_half = bars + 18;   // 256 arrivals: kv rows [0,16) of every 32-row group of dS^T are in shared memory
   uint64_t* dv_full = bars + 17;   // the last dV MMA has completed: the dV epilogue overlaps the last dQ / dK MMAs
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NUM_BARS);
 
@@ -180,7 +174,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     mbar_init(do_full, 1); mbar_init(do_empty, 1);
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(ds_empty, 1);
-    mbar_init(dq_full, 1); mbar_init(dq_empty, 128); mbar_init(dkv_full, 1); mbar_init(dv_full, 1); mbar_init(ds_half, 256);
+    mbar_init(dq_full, 1); mbar_init(dq_empty, 128); mbar_init(dkv_full, 1); mbar_init(dv_full, 1);
     fence_mbar_init();
     fence_proxy_async_smem();
     mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
@@ -297,23 +291,12 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           __syncwarp();
         }
         // dQ_i = dS K first (its consumers, the reducer warps, then drain TMEM while dK executes) ;  dK += dS^T Q_i
-#if FASN_BWD_SPLIT_DS
-        mbar_wait(ds_half, it & 1);
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int kb = 0; kb < 8; kb += 2)
-            umma_ss(tm + TM_DQ, umma_desc_join(sb + oDS + MN + kb * (2048 >> 4), hi_desc), umma_desc_join(sb + oK + MN + kb * (2048 >> 4), hi_desc),
-                    idesc_dq, kb > 0 ? 1u : 0u);
-        }
-        __syncwarp();
-#endif
         mbar_wait(ds_full, it & 1);
         tc_fence_after();
         TL(4);
         if (elect_one()) {
 #pragma unroll
-          for (int kb = FASN_BWD_SPLIT_DS ? 1 : 0; kb < 8; kb += FASN_BWD_SPLIT_DS ? 2 : 1)
+          for (int kb = 0; kb < 8; ++kb)
             umma_ss(tm + TM_DQ, umma_desc_join(sb + oDS + MN + kb * (2048 >> 4), hi_desc), umma_desc_join(sb + oK + MN + kb * (2048 >> 4), hi_desc),
                     idesc_dq, kb > 0 ? 1u : 0u);
           tc_commit(dq_full);
@@ -545,9 +528,6 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               *reinterpret_cast<uint32_t*>(ds_base + j * (8 * 128) + choff) = pack2<BF16>(s01.x, s01.y);
             }
           }
-#if FASN_BWD_SPLIT_DS
-          if (h16 == 0) { fence_proxy_async_smem(); mbar_arrive(ds_half); }
-#endif
         }
         tc_fence_before();
         fence_proxy_async_smem();
@@ -707,9 +687,6 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         tc_fence_before();
         fence_proxy_async_smem();
-#if FASN_BWD_SPLIT_DS
-        mbar_arrive(ds_half);
-#endif
         mbar_arrive(ds_full);
         TL(15);
       }

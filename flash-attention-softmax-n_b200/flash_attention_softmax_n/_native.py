@@ -51,7 +51,7 @@ class FasnParams(ctypes.Structure):
 
 EXPORTS = ("fasn_version", "fasn_last_error", "fasn_fwd", "fasn_bwd", "fasn_bwd_workspace",
            "fasn_dropout_mask", "fasn_probe", "fasn_attention_host", "fasn_profile", "fasn_profile_read",
-           "fasn_softmax_n_fwd", "fasn_softmax_n_bwd")
+           "fasn_softmax_n_fwd", "fasn_softmax_n_bwd", "fasn_copy_async")
 
 _lib: Optional[ctypes.CDLL] = None
 _lock = threading.Lock()
@@ -114,6 +114,8 @@ def load() -> ctypes.CDLL:
         lib.fasn_profile_read.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32),
                                           ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)]
         lib.fasn_profile_read.restype = ctypes.c_int
+        lib.fasn_copy_async.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
+        lib.fasn_copy_async.restype = ctypes.c_int
         v = lib.fasn_version()
         if v != FASN_ABI_VERSION:
             raise FasnError(f"libfasn.so ABI version {v} != binding version {FASN_ABI_VERSION}")

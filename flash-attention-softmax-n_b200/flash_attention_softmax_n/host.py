@@ -16,6 +16,67 @@ from torch import Tensor
 from flash_attention_softmax_n.core.flash_attn import flash_attention_n
 
 
+def bind_process_to_gpu(device_index: int) -> dict:
+    """Pin the calling process to the CPUs that sit next to GPU `device_index` (NVML's CPU affinity of the device), so
+    that pinned host buffers allocated afterwards are first touched -- and therefore placed -- on that GPU's NUMA node and
+    the copy threads run there.  With several ranks on one host every rank otherwise inherits the same default CPU set and
+    all host<->device traffic crosses one memory controller / socket link.  Returns what was done (for bench reports)."""
+    import os
+    info = {"gpu": device_index, "cpus_before": len(os.sched_getaffinity(0))}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1}
+        cpus &= os.sched_getaffinity(0) or cpus
+        try:
+            info["numa_node"] = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            info["numa_node"] = None
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, cpus=len(cpus), cpu_range=f"{min(cpus)}-{max(cpus)}")
+        else:
+            info.update(bound=False, reason="NVML reports no CPU affinity for this GPU")
+    except Exception as e:      # no NVML, or a restricted container: report and carry on unbound
+        info.update(bound=False, reason=f"{type(e).__name__}: {e}"[:200])
+    return info
+
+
+def pinned_copy_rates(device: torch.device, h_in: Tensor, h_out: Tensor, mbytes: int = 256):
+    """(H2D alone, D2H alone, both directions at once: sum) in GB/s for `mbytes` of pinned memory per direction, timed with
+    CUDA events on two streams.  `h_in` / `h_out` are pinned host tensors at least that large."""
+    n = min(mbytes << 20, h_in.numel() * h_in.element_size(), h_out.numel() * h_out.element_size())
+    src = h_in.view(-1).view(torch.uint8)[:n]
+    dst = h_out.view(-1).view(torch.uint8)[:n]
+    d0 = torch.empty(n, dtype=torch.uint8, device=device)
+    d1 = torch.empty(n, dtype=torch.uint8, device=device)
+    s_in, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+
+    def timed(do_in: bool, do_out: bool) -> float:
+        torch.cuda.synchronize(device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        s_in.wait_event(a); s_out.wait_event(a)
+        for _ in range(3):
+            if do_in:
+                with torch.cuda.stream(s_in):
+                    d0.copy_(src, non_blocking=True)
+            if do_out:
+                with torch.cuda.stream(s_out):
+                    dst.copy_(d1, non_blocking=True)
+        cur = torch.cuda.current_stream(device)
+        cur.wait_stream(s_in); cur.wait_stream(s_out)
+        b.record()
+        torch.cuda.synchronize(device)
+        return 3 * n * (int(do_in) + int(do_out)) / (a.elapsed_time(b) * 1e-3) / 1e9
+
+    timed(True, True)
+    return timed(True, False), timed(False, True), timed(True, True)
+
+
 class HostPipeline:
     """Reusable buffers + streams for `attention_host`.  One instance per (shape, dtype, device)."""
 
@@ -37,6 +98,11 @@ class HostPipeline:
     def run(self, q: Tensor, k: Tensor, v: Tensor, dout: Optional[Tensor], o: Tensor,
             grads: Optional[Tuple[Tensor, Tensor, Tensor]], **kw) -> None:
         """q,k,v,dout,o,grads: pinned host tensors shaped (units, rows, D).  Blocks until the outputs are on the host."""
+        if kw.get("dropout_p", 0.0) > 0.0 and kw.get("_philox") is None:
+            # one (seed, offset) per logical call: with the global unit index (`_bh_offset`) the dropout mask is then the
+            # same whatever `chunks` is
+            from flash_attention_softmax_n.core.flash_attn import _next_philox
+            kw = dict(kw, _philox=_next_philox(self.device))
         cur = torch.cuda.current_stream(self.device)
         for st in (self.h2d, self.comp, self.d2h):
             st.wait_stream(cur)

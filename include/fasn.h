@@ -148,6 +148,12 @@ int fasn_softmax_n_fwd(const void* x, void* y, int64_t rows, int32_t cols, int64
 int fasn_softmax_n_bwd(const void* y, const void* dy, void* dx, int64_t rows, int32_t cols, int64_t y_row_stride,
                        int64_t dy_row_stride, int64_t dx_row_stride, uint32_t dtype_in, uint32_t dtype_out, void* stream);
 
+/* Asynchronous copy of `bytes` between any two device (or pinned host) buffers on `stream`: cudaMemcpyAsync with
+ * cudaMemcpyDefault.  parallel.py moves (batch, head) slabs between GPUs with it, through peer memory mapped by CUDA IPC
+ * handles: the copy engines of the issuing device do the transfer over NVLink (measured 790 GB/s per direction between two
+ * B200s; a framework-level tensor copy into IPC-mapped memory took a 35 GB/s path). */
+int fasn_copy_async(void* dst, const void* src, uint64_t bytes, void* stream);
+
 /* Host-buffer convenience used for end-to-end measurement: copies q,k,v (and dout) from HOST memory,
  * runs fwd (+bwd when dout_host != NULL) and copies o (and dq,dk,dv) back.  Contiguous (B,H,S,D) layouts.
  * Uses an internal device arena sized on first use; synchronises `stream` before returning. */

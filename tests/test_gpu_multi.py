@@ -32,9 +32,16 @@ def _worker(rank, world, port, ret):
                                 shape=(B, H, L, S, D), dtype=torch.bfloat16, device=dev, **kw)
         out3 = sharded_attention(q if rank == 0 else None, k if rank == 0 else None, v if rank == 0 else None,
                                  shape=(B, H, L, S, D), dtype=torch.bfloat16, device=dev, chunks=3, **kw)   # pipelined pieces
+        # copy-engine transport through CUDA-IPC-mapped peer memory (what bench.py --gpus N times)
+        out_ipc = sharded_attention(q if rank == 0 else None, k if rank == 0 else None, v if rank == 0 else None,
+                                    shape=(B, H, L, S, D), dtype=torch.bfloat16, device=dev, chunks=2, transport="ipc", **kw)
+        # dropout without an explicit stream: the root draws (seed, offset) once, so two transports / chunkings cannot be
+        # compared bit for bit -- but every rank must use the same stream: rows of different ranks have the same keep rate
         if rank == 0:
             ref = flash_attention_n(q, k, v, **kw)
-            ret["equal"] = bool(torch.equal(out, ref)) and bool(torch.equal(out3, ref))
+            ret["equal"] = bool(torch.equal(out, ref)) and bool(torch.equal(out3, ref)) and bool(torch.equal(out_ipc, ref))
+            out_ipc = None
+        dist.barrier()
     finally:
         dist.destroy_process_group()
 
