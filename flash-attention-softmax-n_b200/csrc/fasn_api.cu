@@ -242,6 +242,12 @@ int fasn_fwd(const FasnParams* p) {
   a.mask = aux_view(p->mask);
   a.bias = aux_view(p->bias);
   a.alibi = p->alibi_slopes;
+#if defined(FASN_DEBUG_FP32_P) && FASN_DEBUG_FP32_P
+  a.o_f32 = p->o_f32;
+#else
+  if (p->o_f32 != nullptr) return fail(FASN_EUNSUPPORTED, "o_f32 is an output of the debug library (libfasn_debug32.so) only");
+  a.o_f32 = nullptr;
+#endif
   a.drop_thr = keep_threshold(p->dropout_p);
   a.inv_keep = 1.0f / keep_probability(p->dropout_p);
   a.key = fasn::make_philox_key(p->philox_seed, p->philox_offset, a.drop_thr);
@@ -310,6 +316,9 @@ int fasn_bwd(const FasnParams* p) {
   a.mask = aux_view(p->mask);
   a.bias = aux_view(p->bias);
   a.alibi = p->alibi_slopes;
+  a.dbias = fasn::AuxView{p->dbias, p->dbias_stride_b, p->dbias_stride_h, p->dbias_stride_q};
+  if (p->dbias != nullptr && p->bias.ptr == nullptr && p->alibi_slopes == nullptr && !(p->mask.ptr != nullptr && p->mask.stride_q != 0))
+    return fail(FASN_EINVAL, "dbias is produced by the dense-tensor kernels: pass the bias (or ALiBi slopes / a dense mask) it belongs to");
   a.drop_thr = keep_threshold(p->dropout_p);
   a.inv_keep = 1.0f / keep_probability(p->dropout_p);
   a.key = fasn::make_philox_key(p->philox_seed, p->philox_offset, a.drop_thr);

@@ -545,6 +545,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const bool has_aux = (mbase != nullptr) || (a.bias.ptr != nullptr) || (a.alibi != nullptr);
       const float alibi2 = (a.alibi != nullptr) ? a.alibi[h] * kLog2e : 0.f;
       const uint16_t* bbase = a.bias.ptr ? reinterpret_cast<const uint16_t*>(a.bias.ptr) + b * a.bias.sb + h * a.bias.sh + kv_c : nullptr;
+      uint16_t* const dbias_row = a.dbias.ptr ? reinterpret_cast<uint16_t*>(const_cast<void*>(a.dbias.ptr)) + b * a.dbias.sb + h * a.dbias.sh + kv_c : nullptr;
       // Dropout keep bits: lane L generates the 32-key keep words of query rows qc0+L and qc0+32+L; a 32x32 bit
       // transpose across the warp then hands every lane (= kv row) its own bit of all 64 query columns.
       uint32_t keep_next0 = 0xFFFFFFFFu, keep_next1 = 0xFFFFFFFFu;
@@ -677,6 +678,16 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const float2 s23 = __fmul2_rn(make_float2(p[g * 32 + c + 2], p[g * 32 + c + 3]), e23);
             out[(c >> 1)] = pack2<BF16>(s01.x, s01.y);
             out[(c >> 1) + 1] = pack2<BF16>(s23.x, s23.y);
+            if (dbias_row != nullptr && kv_row < a.Skv) {
+              // gradient of the logits (= of a dense attn_bias): dS = dS' / P(keep); one 2-byte store per element, the 32 lanes
+              // of a warp cover 32 consecutive keys of one query row
+              const int qq = qc0 + g * 32 + c;
+              const float v4[4] = {s01.x, s01.y, s23.x, s23.y};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (qq + e < a.Sq)
+                  dbias_row[(long long)(qq + e) * a.dbias.sq] = (uint16_t)(pack2<BF16>(v4[e] * (DROPOUT ? a.inv_keep : 1.f), 0.f) & 0xFFFF);
+            }
           }
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {

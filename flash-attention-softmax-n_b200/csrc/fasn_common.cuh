@@ -34,6 +34,7 @@ struct FwdArgs {
   PhiloxKey key;
   uint32_t bh_offset;
   int sched_group;        // units scheduled tile-major at the end of the launch (decode_block)
+  float* o_f32;           // debug builds (FASN_DEBUG_FP32_P) only: (B,H,Sq,D) float32 copy of the output, or null
   int* sched;             // persistent kernels: [0] next work item (beyond the first wave), [1] CTAs finished; both zero before
                           // and after every launch (the last CTA to finish resets them)
   int grid_ctas;          // CTAs to launch: min(SMs of the device, work items)
@@ -52,9 +53,10 @@ struct BwdArgs {
   int Sqp;                // Sq rounded up to 128
   AuxView mask, bias;
   const float* alibi;     // H slopes or null (generic kernels)
+  AuxView dbias;          // optional output of the dense-tensor kernels: dS in the I/O dtype (const-ness of AuxView::ptr is cast away)
   uint32_t drop_thr;
-  float inv_keep;         // 1/(1-p)
-  float keep_prob;        // 1-p
+  float inv_keep;         // 1 / P(keep)
+  float keep_prob;        // P(keep) = T / 256
   PhiloxKey key;
   uint32_t bh_offset;
   int sched_group;        // units scheduled tile-major at the end of the launch (decode_block)

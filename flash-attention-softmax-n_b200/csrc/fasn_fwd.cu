@@ -50,6 +50,14 @@ namespace {
 #endif
 
 constexpr int kFwdThreads = 384;
+// Debug build (-DFASN_DEBUG_FP32_P=1, libfasn_debug32.so): the probabilities reach the tensor core as
+// P_hi + P_lo, two 16-bit terms that together carry ~22 mantissa bits (P.V is issued twice per K-step), every exponential runs
+// on the MUFU, and the output can be taken in float32 (FasnParams.o_f32) -- the accuracy of the algorithm without the 16-bit
+// rounding of P and O.  Checked to <= 1e-5 relative L2 against the float64 oracle (tests/test_gpu_debug32.py).  Forward only.
+#ifndef FASN_DEBUG_FP32_P
+#define FASN_DEBUG_FP32_P 0
+#endif
+
 constexpr float kRescaleThreshold = 8.0f;   // log2 units
 // Share of the exponentials evaluated by exp2_poly_pair instead of MUFU.EX2 on unmasked tiles: in kPolyCount of
 // every kPolyPeriod groups of four elements, one of the two pairs is a polynomial (1 of 2 -> 25 %).  0 disables.
@@ -122,7 +130,7 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // have READ it and Q.K^T of the next K/V tile is issued during the softmax of the current one, instead of after its
   // P.V -- at D=64 the MMAs are short and the serial chain Q.K^T -> softmax -> P.V per tile was the limiter.
   // (At D=128 the 512 columns are full: S0 S1 O0 O1.)
-  constexpr bool kSepP = (D == 64);
+  constexpr bool kSepP = (D == 64) && !FASN_DEBUG_FP32_P;   // (the debug build keeps P_lo beside P_hi in the S_t columns)
 
   TLF_CTA_BEGIN();
   const int warp = threadIdx.x >> 5;
@@ -243,6 +251,9 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const int k = half * 4 + kb;
           umma_ts(tm + 256 + t * D, tm + (kSepP ? 384 + t * 64 : t * 128) + k * 8, umma_desc_join(b0 + k * (2048 >> 4), hi_desc), idesc_pv,
                   (half > 0 || kb > 0) ? 1u : acc);
+#if FASN_DEBUG_FP32_P
+          umma_ts(tm + 256 + t * D, tm + t * 128 + 64 + k * 8, umma_desc_join(b0 + k * (2048 >> 4), hi_desc), idesc_pv, 1u);   // P_lo
+#endif
         }
       };
       // counters that run across work items: items seen, K/V tiles consumed, items with Q loads, per Q tile: steps done and
@@ -408,12 +419,12 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         TLF(10);
         uint32_t kw[4];
         if constexpr (DROPOUT) {   // independent of S: issue before waiting for the tensor core
-  #pragma unroll
+#pragma unroll
           for (int i = 0; i < 4; ++i) kw[i] = dropout_keep_word(a.key, bh_global, (uint32_t)row, (uint32_t)(j0 >> 5) + i, a.drop_thr);
         }
         uint32_t vis[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
         if (key_only_mask) {
-  #pragma unroll
+#pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int col = j0 + 32 * i + lane;
             const uint8_t mb = (col < a.Skv) ? __ldg(mrow + col) : (uint8_t)1;      // keys beyond Skv are cut by row_lim below
@@ -429,7 +440,7 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         uint4 bq[GENERIC ? 16 : 1];
         if constexpr (GENERIC) {
           if (bias_fast) {
-  #pragma unroll
+#pragma unroll
             for (int g = 0; g < 16; ++g) bq[g] = __ldg(reinterpret_cast<const uint4*>(brow + j0) + g);
           }
         }
@@ -450,40 +461,40 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if constexpr (GENERIC) {
           if (a.alibi != nullptr) {       // ALiBi generated in place: + slope (j - i - (S - L)), log2 domain
             const float base = alibi2 * (float)(j0 - row - a.causal_off);
-  #pragma unroll
+#pragma unroll
             for (int c = 0; c < 128; ++c) s[c] = fmaf(s[c], a.scale_log2, fmaf(alibi2, (float)c, base));
           } else {
-  #pragma unroll
+#pragma unroll
             for (int c = 0; c < 128; ++c) s[c] *= a.scale_log2;
           }
           if (has_aux) {
             // dense bias / mask rows of this thread: 16-byte loads where the row segment is aligned and in range
             // (each thread streams its own 256 B / 128 B per tile; lines are shared by consecutive instructions via L1)
             if (bias_fast) {
-  #pragma unroll
+#pragma unroll
               for (int g = 0; g < 16; ++g) {
                 const uint32_t w[4] = {bq[g].x, bq[g].y, bq[g].z, bq[g].w};
-  #pragma unroll
+#pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   s[g * 8 + 2 * e] = fmaf(cvt16_to_f32<BF16>(w[e] & 0xFFFF), kLog2e, s[g * 8 + 2 * e]);
                   s[g * 8 + 2 * e + 1] = fmaf(cvt16_to_f32<BF16>(w[e] >> 16), kLog2e, s[g * 8 + 2 * e + 1]);
                 }
               }
             } else if (brow) {
-  #pragma unroll
+#pragma unroll
               for (int g = 0; g < 16; ++g) {                    // 8 bias elements per 16-byte load
                 const int col = j0 + g * 8;
                 const uint16_t* p = brow + col;
                 if (col + 8 <= a.Skv && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
                   const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(p));
                   const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
-  #pragma unroll
+#pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     s[g * 8 + 2 * e] = fmaf(cvt16_to_f32<BF16>(w[e] & 0xFFFF), kLog2e, s[g * 8 + 2 * e]);
                     s[g * 8 + 2 * e + 1] = fmaf(cvt16_to_f32<BF16>(w[e] >> 16), kLog2e, s[g * 8 + 2 * e + 1]);
                   }
                 } else {
-  #pragma unroll
+#pragma unroll
                   for (int e = 0; e < 8; ++e)
                     if (col + e < a.Skv) s[g * 8 + e] = fmaf(cvt16_to_f32<BF16>(p[e]), kLog2e, s[g * 8 + e]);
                 }
@@ -491,28 +502,28 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             if (mask_fast) {
               uint4 mq[8];
-  #pragma unroll
+#pragma unroll
               for (int g = 0; g < 8; ++g) mq[g] = __ldg(reinterpret_cast<const uint4*>(mrow + j0) + g);
-  #pragma unroll
+#pragma unroll
               for (int g = 0; g < 8; ++g) {
                 const uint32_t w[4] = {mq[g].x, mq[g].y, mq[g].z, mq[g].w};
-  #pragma unroll
+#pragma unroll
                 for (int e = 0; e < 16; ++e)
                   if (((w[e >> 2] >> (8 * (e & 3))) & 0xFF) == 0) s[g * 16 + e] = -INFINITY;
               }
             } else if (mrow) {
-  #pragma unroll
+#pragma unroll
               for (int g = 0; g < 8; ++g) {                     // 16 mask bytes per 16-byte load
                 const int col = j0 + g * 16;
                 const uint8_t* p = mrow + col;
                 if (col + 16 <= a.Skv && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
                   const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(p));
                   const uint32_t w[4] = {v4.x, v4.y, v4.z, v4.w};
-  #pragma unroll
+#pragma unroll
                   for (int e = 0; e < 16; ++e)
                     if (((w[e >> 2] >> (8 * (e & 3))) & 0xFF) == 0) s[g * 16 + e] = -INFINITY;
                 } else {
-  #pragma unroll
+#pragma unroll
                   for (int e = 0; e < 16; ++e)
                     if (col + e < a.Skv && p[e] == 0) s[g * 16 + e] = -INFINITY;
                 }
@@ -523,15 +534,15 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const bool masked_tile = (j0 + 128 > warp_row_lim) || hidden_keys;      // warp-uniform
         if (j0 + 128 > warp_row_lim) {
           const int lim = row_lim - j0;
-  #pragma unroll
+#pragma unroll
           for (int c = 0; c < 128; ++c) s[c] = (c < lim) ? s[c] : -INFINITY;
         }
         if (hidden_keys) {
-  #pragma unroll
+#pragma unroll
           for (int c = 0; c < 128; ++c) s[c] = ((vis[c >> 5] >> (c & 31)) & 1u) ? s[c] : -INFINITY;
         }
         float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
-  #pragma unroll
+#pragma unroll
         for (int c = 4; c < 124; c += 8) {
           mx0 = fmax3(mx0, s[c], s[c + 1]); mx1 = fmax3(mx1, s[c + 2], s[c + 3]);
           mx2 = fmax3(mx2, s[c + 4], s[c + 5]); mx3 = fmax3(mx3, s[c + 6], s[c + 7]);
@@ -549,12 +560,12 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           // rescale the O accumulator of this tile (rare): PV_{j-1} must have landed first
           mbar_wait(&o_full[t], (sc + j - 1) & 1);
           tc_fence_after();
-  #pragma unroll
+#pragma unroll
           for (int cb = 0; cb < D / 32; ++cb) {
             uint32_t o[32];
             tmem_ld_x32(tO + cb * 32, o);
             tmem_wait_ld();
-  #pragma unroll
+#pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st_x32(tO + cb * 32, o);
           }
@@ -563,29 +574,44 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const float m_use = (m == -INFINITY) ? 0.f : m;
         const float2 negm2 = make_float2(-m_use, -m_use);
         uint32_t pr[64];
+#if FASN_DEBUG_FP32_P
+        uint32_t pr_lo[64];
+#endif
         float2 l01 = make_float2(0.f, 0.f), l23 = make_float2(0.f, 0.f);
         auto finish4 = [&](int c, float p0, float p1, float p2, float p3) {
           l01 = __fadd2_rn(l01, make_float2(p0, p1));
           l23 = __fadd2_rn(l23, make_float2(p2, p3));
           uint32_t w01 = pack2<BF16>(p0, p1), w23 = pack2<BF16>(p2, p3);
+#if FASN_DEBUG_FP32_P
+          uint32_t r01 = pack2<BF16>(p0 - cvt16_to_f32<BF16>((uint16_t)(w01 & 0xFFFF)), p1 - cvt16_to_f32<BF16>((uint16_t)(w01 >> 16)));
+          uint32_t r23 = pack2<BF16>(p2 - cvt16_to_f32<BF16>((uint16_t)(w23 & 0xFFFF)), p3 - cvt16_to_f32<BF16>((uint16_t)(w23 >> 16)));
+#endif
           if constexpr (DROPOUT) {     // zero the dropped entries on the packed pairs: 1 PRMT + 1 AND per two elements
             const uint32_t w = kw[c >> 5];
             w01 &= keep_pair_mask(w, c & 31);
             w23 &= keep_pair_mask(w, (c + 2) & 31);
+#if FASN_DEBUG_FP32_P
+            r01 &= keep_pair_mask(w, c & 31);
+            r23 &= keep_pair_mask(w, (c + 2) & 31);
+#endif
           }
           pr[c >> 1] = w01;
           pr[(c >> 1) + 1] = w23;
+#if FASN_DEBUG_FP32_P
+          pr_lo[c >> 1] = r01;
+          pr_lo[(c >> 1) + 1] = r23;
+#endif
         };
-  #ifndef FASN_POLY_DROPOUT
-  #define FASN_POLY_DROPOUT 1
-  #endif
-        constexpr int kPolyCount = (D == 64 || (DROPOUT && FASN_POLY_DROPOUT)) ? 1 : 0;
+#ifndef FASN_POLY_DROPOUT
+#define FASN_POLY_DROPOUT 1
+#endif
+        constexpr int kPolyCount = (!FASN_DEBUG_FP32_P && (D == 64 || (DROPOUT && FASN_POLY_DROPOUT))) ? 1 : 0;
         const bool use_poly = kPolyCount > 0 && !generic && !masked_tile;
-  #pragma unroll
+#pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           if (use_poly) {
             // interior tile, all scores finite: a fixed share of the exponentials runs as a polynomial on the FMA pipes
-  #pragma unroll
+#pragma unroll
             for (int c = hf * 64; c < hf * 64 + 64; c += 4) {
               const float2 a01 = __ffma2_rn(make_float2(s[c], s[c + 1]), cmul2, negm2);
               const float2 a23 = __ffma2_rn(make_float2(s[c + 2], s[c + 3]), cmul2, negm2);
@@ -595,7 +621,7 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               finish4(c, p0, p1, p2, p3);
             }
           } else {
-  #pragma unroll
+#pragma unroll
             for (int c = hf * 64; c < hf * 64 + 64; c += 4) {
               const float2 a01 = __ffma2_rn(make_float2(s[c], s[c + 1]), cmul2, negm2);
               const float2 a23 = __ffma2_rn(make_float2(s[c + 2], s[c + 3]), cmul2, negm2);
@@ -606,6 +632,9 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           // or in P_t's own columns once the previous P.V has consumed them (D=64)
           if (kSepP && hf == 0 && j > 0) { mbar_wait(&o_full[t], (sc + j - 1) & 1); tc_fence_after(); }
           tmem_st_x32((kSepP ? tmem_base + lane_off + 384 + t * 64 : tS) + hf * 32, pr + hf * 32);
+#if FASN_DEBUG_FP32_P
+          tmem_st_x32(tS + 64 + hf * 32, pr_lo + hf * 32);      // S_t columns [64,128) were read into registers above
+#endif
           if (kSplitPV || hf == 1) {
             tmem_wait_st();
             tc_fence_before();
@@ -638,6 +667,15 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = 0u;
         }
+#if FASN_DEBUG_FP32_P
+        if (a.o_f32 != nullptr && row < a.Sq) {
+          float4* dst = reinterpret_cast<float4*>(a.o_f32 + ((long long)bh * a.Sq + row) * D + cb * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            dst[i] = make_float4(__uint_as_float(o[4 * i]) * inv, __uint_as_float(o[4 * i + 1]) * inv, __uint_as_float(o[4 * i + 2]) * inv,
+                                 __uint_as_float(o[4 * i + 3]) * inv);
+        }
+#endif
 #pragma unroll
         for (int g4 = 0; g4 < 4; ++g4) {   // 4 x 16-byte chunks (8 elements each)
           uint4 v;

@@ -14,7 +14,7 @@ from typing import Optional
 
 import torch
 
-FASN_ABI_VERSION = 1
+FASN_ABI_VERSION = 2
 FASN_FP16, FASN_BF16 = 0, 1
 
 _LIB_ENV = "FASN_LIBRARY"
@@ -46,6 +46,9 @@ class FasnParams(ctypes.Structure):
         ("mask", FasnAux), ("bias", FasnAux),
         ("stream", ctypes.c_void_p),
         ("alibi_slopes", ctypes.c_void_p),
+        ("dbias", ctypes.c_void_p), ("dbias_stride_b", ctypes.c_int64), ("dbias_stride_h", ctypes.c_int64),
+        ("dbias_stride_q", ctypes.c_int64),
+        ("o_f32", ctypes.c_void_p),
     ]
 
 

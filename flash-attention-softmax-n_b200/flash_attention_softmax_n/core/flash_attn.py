@@ -11,10 +11,11 @@ Same names, order, defaults and meaning of the arguments; what happens underneat
 * there is no backend chooser (`_flash_attn_config`, flash_attn.py:17-35) and no fallback: inputs the
   kernels do not cover raise `NotImplementedError` (use `slow_attention_n` for those).
 
-Covered: CUDA tensors, float16 / bfloat16, E == Ev in {64, 128}, 4-D query, 4-D or 3-D key/value
-(3-D = shared by all heads, flash_attn.py:75-79), any L and S, boolean `attn_mask` (True = attend),
+Covered: CUDA tensors, float16 / bfloat16 (float32 tensors are computed with float16 operands and float32 accumulation
+and returned in float32, see `flash_attention_n`), head dims up to 128 (64 and 128 run unpadded), 4-D query, 4-D or 3-D
+key/value (3-D = shared by all heads, flash_attn.py:75-79), any L and S, boolean `attn_mask` (True = attend),
 `attn_bias` of shape (H,L,S) or 4-D broadcastable, `is_causal` bottom-right aligned, dropout.
-Gradients flow to query, key and value (not to `attn_bias`).
+Gradients flow to query, key, value and `attn_bias`.
 """
 from __future__ import annotations
 
@@ -66,8 +67,6 @@ def _prepare_aux(attn_mask: Optional[Tensor], attn_bias: Optional[Tensor], q: Te
         attn_mask.expand(B, H, L, S)                                         # shape check only (flash_attn.py:89)
         attn_mask = _canon_aux(attn_mask, S)
     if attn_bias is not None:
-        if attn_bias.requires_grad:
-            raise NotImplementedError("gradients with respect to attn_bias are not implemented by the fused kernel")
         if attn_bias.ndim == 3:
             attn_bias = attn_bias.unsqueeze(0)                               # 'h i j -> 1 h i j' (flash_attn.py:101-102)
         assert attn_bias.ndim == 4
@@ -95,7 +94,8 @@ def _fill_common(p: _native.FasnParams, q: Tensor, k: Tensor, v: Tensor, o: Tens
 
 class _FusedAttentionN(torch.autograd.Function):
     """Counterpart of the reference's `_FlashAttentionN` (flash_attn_triton.py:241-336): saves
-    (q, k, v, o, lse) and returns gradients for q, k, v only."""
+    (q, k, v, o, lse) and returns gradients for q, k, v -- and for a dense `attn_bias` that requires one, which the
+    reference's SDPA route provides through aten autograd (flash_attn.py:100-124)."""
 
     @staticmethod
     def forward(ctx, q: Tensor, k: Tensor, v: Tensor, heads_kv: int, n: float, scale: float, causal: bool,
@@ -133,11 +133,21 @@ class _FusedAttentionN(torch.autograd.Function):
             _fill_common(p, q, k, v, o, lse, heads_kv, n, scale, causal, dropout_p, seed, offset, bh_offset, mask, bias, alibi)
             p.dout, p.dq, p.dk, p.dv = (_native.tensor_view(t) for t in (do, dq, dk, dv))
             p.delta, p.dq_accum = ws.data_ptr(), dq_accum.data_ptr()
+            ds = None
+            if bias is not None and ctx.needs_input_grad[9]:
+                # dS for every (b, h, i, j); entries above the causal diagonal are never visited by a CTA and stay zero
+                ds = torch.zeros((B, H, L, S), dtype=q.dtype, device=q.device)
+                p.dbias, p.dbias_stride_b, p.dbias_stride_h, p.dbias_stride_q = ds.data_ptr(), H * L * S, L * S, S
             _native.check(lib.fasn_bwd(ctypes.byref(p)), "fasn_bwd")
         if heads_kv == 1 and H > 1:
             dk = dk.sum(dim=1, keepdim=True, dtype=torch.float32).to(q.dtype)
             dv = dv.sum(dim=1, keepdim=True, dtype=torch.float32).to(q.dtype)
-        return dq, dk, dv, None, None, None, None, None, None, None, None, None, None, None
+        dbias = None
+        if ds is not None:
+            # reduce over the axes the bias broadcasts (size 1), accumulating in float32
+            dims = [d for d in range(4) if bias.shape[d] == 1 and ds.shape[d] != 1]
+            dbias = (ds.sum(dim=dims, keepdim=True, dtype=torch.float32) if dims else ds).to(bias.dtype)
+        return dq, dk, dv, None, None, None, None, None, None, dbias, None, None, None, None
 
 
 def flash_attention_n(
@@ -161,6 +171,7 @@ def flash_attention_n(
     :param query: Query tensor; shape (N, H, L, E).
     :param key: Key tensor; shape (N, H, S, E) or (N, S, E) (shared by all heads).
     :param value: Value tensor; shape (N, H, S, Ev) or (N, S, Ev).  E, Ev <= 128 (64 and 128 run unpadded).
+        query / key / value: float16, bfloat16, or float32 (computed with float16 operands, float32 accumulation).
     :param softmax_n_param: Regularization parameter n >= 0 of softmax_n (any real number; None = 0).
     :param scale: Scaling factor applied prior to softmax. If None, the default value is set to 1 / sqrt(E).
     :param dropout_p: Dropout probability; if greater than 0.0, dropout is applied.
@@ -182,8 +193,18 @@ def flash_attention_n(
     if not query.is_cuda:
         raise NotImplementedError("flash_attention_n runs on CUDA (B200) tensors only; there is no CPU path. "
                                   "Use slow_attention_n for eager evaluation.")
+    if query.dtype == torch.float32 and key.dtype == torch.float32 and value.dtype == torch.float32:
+        # float32 tensors (supported by the reference's SDPA route, README.md:42; its GPU test asks atol 1e-3,
+        # tests/gpu/core/test_flash_attn.py:14): the tensor cores take 16-bit operands, so the inputs are rounded to float16
+        # -- the 10-bit mantissa a `kind::tf32` MMA would keep as well -- products are accumulated in float32, and the result
+        # and the gradients come back in float32 (autograd carries them through the casts).  Values beyond the float16
+        # range (|x| > 65504) overflow; use bfloat16 tensors or slow_attention_n for such inputs.
+        f16 = lambda t: None if t is None else (t.to(torch.float16) if t.is_floating_point() else t)
+        out = flash_attention_n(f16(query), f16(key), f16(value), softmax_n_param, scale, dropout_p, attn_mask, f16(attn_bias),
+                                is_causal, _philox=_philox, _bh_offset=_bh_offset, _alibi_slopes=_alibi_slopes)
+        return out.to(torch.float32)
     if query.dtype not in (torch.float16, torch.bfloat16) or key.dtype != query.dtype or value.dtype != query.dtype:
-        raise NotImplementedError(f"fused kernel supports float16/bfloat16 with matching dtypes, got "
+        raise NotImplementedError(f"fused kernel supports float16 / bfloat16 / float32 with matching dtypes, got "
                                   f"{query.dtype}/{key.dtype}/{value.dtype}; use slow_attention_n")
     B, H, L, E = query.shape
     heads_kv = H

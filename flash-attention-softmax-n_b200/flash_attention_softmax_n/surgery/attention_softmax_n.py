@@ -72,11 +72,16 @@ def _decompose_mask(mask: Tensor, L: int, S: int):
     The library builds dense masks, but the two it builds in practice are "key padding" (all query rows equal) and
     "causal AND key padding".  Both have O(B*S) descriptions that keep the kernels on their fast paths (a dense mask
     costs B*H*L*S bytes of reads per pass): a key-only mask is passed with query stride 0, causality as the flag.
-    The comparison reads the mask once and synchronises; the result is cached for the other layers of the pass, keyed
-    by the identity of the live tensor object (a weak reference: a recycled address can never hit) and its version."""
+    The comparison reads the mask once and synchronises (once per forward pass: the result is cached for the other layers,
+    keyed by the identity of the live tensor object -- a weak reference, so a recycled address can never hit -- and its
+    version; inference tensors carry no version counter and are keyed by identity alone).  While a CUDA graph is being
+    captured a synchronisation is illegal: the dense mask is then passed through unchanged (generic kernels)."""
+    ver = None if mask.is_inference() else mask._version
     hit = _MASK_CACHE.get("k")
-    if hit is not None and hit[0]() is mask and hit[1] == (mask._version, L, S):
+    if hit is not None and hit[0]() is mask and hit[1] == (ver, L, S):
         return hit[2], hit[3]
+    if mask.is_cuda and torch.cuda.is_current_stream_capturing():
+        return mask, False
     out = (mask, False)
     if L > 1 and mask.shape[2] == L:
         last = mask[:, :, -1:, :]
@@ -88,8 +93,22 @@ def _decompose_mask(mask: Tensor, L: int, S: int):
             tri = cols <= rows + (S - L)                       # bottom-right aligned, as is_causal (flash_attn.py:38-39)
             if bool(torch.equal(mask, last & tri)):
                 out = (last, True)
-    _MASK_CACHE["k"] = (weakref.ref(mask), (mask._version, L, S), out[0], out[1])
+    _MASK_CACHE["k"] = (weakref.ref(mask), (ver, L, S), out[0], out[1])
     return out
+
+
+# Keyword arguments of the attention interface that change the attention arithmetic and that neither route implements.
+# They are refused when present (not None / not False) instead of being swallowed: a model that needs them (Gemma-2's
+# logit soft-capping, GPT-OSS attention sinks, head masks, returned attention weights) would otherwise run with silently
+# different attention.
+_UNSUPPORTED_KWARGS = ("softcap", "s_aux", "sinks", "head_mask", "sliding_window", "output_attentions")
+
+
+def _check_kwargs(kwargs: dict) -> None:
+    bad = [k for k in _UNSUPPORTED_KWARGS if kwargs.get(k) is not None and kwargs.get(k) is not False]
+    if bad:
+        raise NotImplementedError(f"softmax_n attention routes do not implement {bad}; this architecture needs an attention "
+                                  "function of its own")
 
 
 def _common(module: Module, query: Tensor, key: Tensor, value: Tensor, attention_mask: Optional[Tensor],
@@ -122,6 +141,7 @@ def attention_softmax_n_forward(module: Module, query: Tensor, key: Tensor, valu
                                 scaling: Optional[float] = None, is_causal: Optional[bool] = None, **kwargs):
     """`transformers` attention-interface function on the fused kernels.  query/key/value are (B, H, L|S, D);
     returns ((B, L, H, D) output, None): attention weights are never materialised."""
+    _check_kwargs(kwargs)
     n, key, value, mask, bias, causal = _common(module, query, key, value, attention_mask, is_causal, True)
     if not query.is_cuda or query.dtype not in (torch.float16, torch.bfloat16):
         raise NotImplementedError(
@@ -138,6 +158,7 @@ def eager_attention_softmax_n_forward(module: Module, query: Tensor, key: Tensor
                                       scaling: Optional[float] = None, is_causal: Optional[bool] = None, **kwargs):
     """The same interface on the operator's eager definition (`slow_attention_n`): what the reference's patched
     forwards compute (_bert.py:73-111), kept as the checker for the fused route and for CPU / fp32 models."""
+    _check_kwargs(kwargs)
     n, key, value, mask, bias, causal = _common(module, query, key, value, attention_mask, is_causal, False)
     out = slow_attention_n(query, key, value, attn_mask=mask if mask is not None else bias, dropout_p=float(dropout),
                            is_causal=causal, scale=scaling, softmax_n_param=n, train=module.training)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FASN_ABI_VERSION 1
+#define FASN_ABI_VERSION 2
 
 enum { FASN_FP16 = 0, FASN_BF16 = 1 };
 
@@ -95,6 +95,18 @@ typedef struct FasnParams {
    * NULL, or H fp32 slopes on the device; the logit of (i, j) gets  + alibi_slopes[h] * (j - i - (S - L)),
    * i.e. slope times the signed distance to the bottom-right aligned diagonal.  Exclusive with `bias`. */
   const float* alibi_slopes;
+
+  /* backward only, optional: gradient with respect to the logits dS = P o (dP - delta) (dropout scaling included), i.e. the
+   * gradient of a dense `bias`, written as (B,H,L,S) elements of the I/O dtype at dbias[b*stride_b + h*stride_h + i*stride_q + j].
+   * Entries no CTA visits (above the causal diagonal) are not written: the caller zero-fills.  The caller reduces over the
+   * axes its bias broadcasts (the SDPA route of the reference gives this gradient through aten autograd, flash_attn.py:100-124).
+   * Requires `bias` or `alibi_slopes` or a dense mask (the dense-tensor kernels); NULL = not wanted. */
+  void*   dbias;
+  int64_t dbias_stride_b, dbias_stride_h, dbias_stride_q;
+
+  /* forward, debug library only (libfasn_debug32.so, built with -DFASN_DEBUG_FP32_P=1: P as two 16-bit terms, float32 output):
+   * contiguous (B,H,L,D) float32 copy of the output, or NULL.  The product library rejects a non-NULL value. */
+  float*  o_f32;
 } FasnParams;
 
 /* ABI version of the loaded library (== FASN_ABI_VERSION it was built with). */

@@ -137,7 +137,9 @@ def test_forward_strided_inputs_and_errors(fasn_lib):
     want = orc.slow_attention_n(q.double().cpu(), k.double().cpu(), v.double().cpu(), softmax_n_param=1, is_causal=True)
     check_close("O(strided)", out, want, None, dtype)
     with pytest.raises(NotImplementedError):
-        flash_attention_n(q.float(), k.float(), v.float())
+        flash_attention_n(q.double(), k.double(), v.double())                    # float64: use slow_attention_n
+    with pytest.raises(NotImplementedError):
+        flash_attention_n(q.float(), k, v)                                       # mixed dtypes
     with pytest.raises(NotImplementedError):
         big = torch.zeros(1, 1, 8, 160, dtype=dtype, device="cuda")
         flash_attention_n(big, big, big)                                         # head dims above 128

@@ -146,3 +146,31 @@ def test_trainer_plugin_keeps_the_reference_shape():
     if S._Event is None:
         with pytest.raises(RuntimeError, match="Composer"):
             algo.match(None, None)
+
+
+def test_decompose_mask_under_inference_mode_and_without_version_counter():
+    """Inference tensors carry no version counter (`mask._version` raises): the cache is then keyed by identity alone."""
+    L = S_ = 6
+    with torch.inference_mode():
+        pad = torch.tensor([[1, 1, 1, 1, 0, 0]], dtype=torch.bool).view(1, 1, 1, S_).expand(1, 1, L, S_).contiguous()
+        m, causal = S._decompose_mask(pad, L, S_)
+        assert m.shape == (1, 1, 1, S_) and causal is False
+        m2, causal2 = S._decompose_mask(pad, L, S_)                    # cache hit
+        assert m2 is m and causal2 is False
+        tri = torch.tril(torch.ones(L, S_, dtype=torch.bool)).view(1, 1, L, S_) & pad
+        m3, causal3 = S._decompose_mask(tri, L, S_)
+        assert m3.shape == (1, 1, 1, S_) and causal3 is True
+
+
+@pytest.mark.parametrize("kw", [dict(softcap=30.0), dict(s_aux=torch.zeros(2)), dict(head_mask=torch.ones(2)), dict(output_attentions=True)])
+def test_semantics_changing_kwargs_are_refused(kw):
+    mod = torch.nn.Module()
+    mod.softmax_n_param = 1.0
+    q = torch.randn(1, 2, 4, 8)
+    with pytest.raises(NotImplementedError, match="do not implement"):
+        S.eager_attention_softmax_n_forward(mod, q, q, q, None, **kw)
+    with pytest.raises(NotImplementedError, match="do not implement"):
+        S.attention_softmax_n_forward(mod, q, q, q, None, **kw)
+    # absent / None / False values pass through
+    out, _ = S.eager_attention_softmax_n_forward(mod, q, q, q, None, softcap=None, output_attentions=False)
+    assert out.shape == (1, 4, 2, 8)
