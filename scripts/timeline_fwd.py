@@ -22,7 +22,7 @@ torch.cuda.synchronize()
 ev = buf.cpu().view(5, 2048)
 rows = sorted((e & 0xFFFFFFFFFFFF, role, (e >> 48) & 0xFFFF) for role in range(5) for e in ev[role].tolist() if e)
 t0 = rows[0][0]
-names = {0: "mma", 1: "sm0", 2: "sm1"}
+names = {0: "mma", 1: "sm0", 2: "sm1", 3: "gen"}
 with open(os.path.join(ROOT, "gpurun_out", f"timeline_fwd_{tag}.txt"), "w") as f:
     for t, role, tg in rows:
         f.write(f"{t - t0:9d} {names.get(role, role)} {tg}\n")
