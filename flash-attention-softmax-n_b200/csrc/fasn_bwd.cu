@@ -56,6 +56,12 @@ namespace {
 
 
 constexpr int kBwdThreads = 512;
+// K-steps (of 8) of dK_i issued BEFORE dP^T of the next Q tile; the rest follow it.  The MMAs execute in issue order, and
+// the critical path of an iteration is dS_i -> dQ_i -> (drain of dQ_i from tensor memory) -> dP^T_{i+1} -> dS_{i+1}: with all of
+// dK_i queued ahead of dP^T_{i+1} its ~900 cycles sit on that path; only as much of it as fits into the drain belongs there.
+#ifndef FASN_BWD_DK_SPLIT
+#define FASN_BWD_DK_SPLIT 4
+#endif
 // Register budgets after the role split (setmaxnreg): 8 compute warps, 4 dQ reducer warps (the whole fp32 dQ tile row of a
 // thread, D values, lives in registers), 4 producer / MMA / idle warps.  256 x 152 + 128 x 152 + 128 x 56 = 65536 at D = 128,
 // 256 x 176 + 128 x 104 + 128 x 56 = 65536 at D = 64.
@@ -300,16 +306,18 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             umma_ss(tm + TM_DQ, umma_desc_join(sb + oDS + MN + kb * (2048 >> 4), hi_desc), umma_desc_join(sb + oK + MN + kb * (2048 >> 4), hi_desc),
                     idesc_dq, kb > 0 ? 1u : 0u);
           tc_commit(dq_full);
+        }
+        __syncwarp();
+        auto issue_dk = [&](int kb0, int kb1) {
 #pragma unroll
-          for (int kb = 0; kb < 8; ++kb) {
+          for (int kb = kb0; kb < kb1; ++kb) {
             const uint32_t off = ((kb >> 2) * BLK_BYTES + (kb & 3) * 32) >> 4;
             umma_ss(tm + TM_DK, umma_desc_join(sb + oDS + KM + off, hi_desc), umma_desc_join(sb + oQ + MN + s * TILE16 + kb * (2048 >> 4), hi_desc),
                     idesc_dk, (it > 0 || kb > 0) ? 1u : 0u);
           }
-          tc_commit(&q_empty[s]);      // Q_i, LSE2_i and delta_i stay valid until the compute warps are done with tile i
-                                       // (ds_full above) and the MMAs that read Q_i have completed
-          tc_commit(ds_empty);
-        }
+        };
+        constexpr int kSplit = FASN_BWD_DK_SPLIT;
+        if (elect_one()) issue_dk(0, more ? kSplit : 8);
         __syncwarp();
         // dP^T of the next tile reuses the dQ columns: wait until the reducers have drained dQ_i
         if (more) {
@@ -321,6 +329,13 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (elect_one()) { issue_kmajor(TM_DP, sb + oV + KM, sb + oDO + KM); tc_commit(dp_full); }
           __syncwarp();
         }
+        if (elect_one()) {
+          if (more) issue_dk(kSplit, 8);
+          tc_commit(&q_empty[s]);      // Q_i, LSE2_i and delta_i stay valid until the compute warps are done with tile i
+                                       // (ds_full above) and the MMAs that read Q_i have completed
+          tc_commit(ds_empty);
+        }
+        __syncwarp();
       }
       if (elect_one()) tc_commit(dkv_full);
       __syncwarp();
