@@ -324,6 +324,12 @@ int fasn_bwd(const FasnParams* p) {
   a.key = fasn::make_philox_key(p->philox_seed, p->philox_offset, a.drop_thr);
   a.bh_offset = (uint32_t)p->bh_offset;
   a.sched_group = fasn::sched_group_size(2ll * D * (2ll * L + 2ll * S) + 4ll * D * L);   // Q, dO, K, V + the fp32 dQ accumulator
+  {
+    int num_sms = 0;
+    if (int rc = sched_slot(&a.sched, &num_sms)) return rc;
+    const long long items = (long long)B * H * ((S + 127) / 128);
+    a.grid_ctas = (int)(items < num_sms ? items : num_sms);
+  }
 #ifdef FASN_TIMELINE
   {
     extern unsigned long long* g_fasn_timeline; extern unsigned int g_fasn_timeline_xy[2];

@@ -26,7 +26,15 @@
 //               port cycles per tile pair)
 //   warps 8-11  dQ reducers: TMEM -> registers -> fp32 staging in smem -> TMA reduce-add
 //   warp 12     TMA producer (K,V once; Q_i + LSE2 + delta through a 2-deep ring, dO_i single-buffered)
-//   warp 13     MMA issuer (one elected lane)  warp 14  TMEM allocator        warp 15  idle
+//   warp 13     MMA issuer (one elected lane)  warp 14  TMEM allocator        warp 15  issues the dV / dK stores of the epilogue
+//
+// Persistent: the grid is one CTA per SM; every CTA takes (K/V tile, unit) work items from a global counter in the heavy-first
+// order of decode_block until they run out.  Barrier set-up, tensor-memory allocation and the launch gap are paid once per SM,
+// and the head of the next item overlaps the tail of the current one: Q / dO of its first tile are loaded as soon as the ring
+// slot / the dO buffer is free, K as soon as the last dQ MMA has completed (dK is staged in the dS^T tile, not in sK), V as soon
+// as the TMA store of dV has read its staging tile (sV; warp 15 issues the epilogue stores and waits for them, so no compute
+// thread does), and S^T / dP^T of the first tile are issued while the compute warps are still draining dK.  Per-CTA overhead was 9760 cycles + a 770 ns launch gap per item against 4718 cycles per Q tile
+// (12 % of the C3 backward, scripts/cta_profile.py).
 #include "fasn_common.cuh"
 #include "fasn_ptx.cuh"
 
@@ -37,7 +45,7 @@ namespace {
 // Optional phase timeline (compile with -DFASN_TIMELINE): one CTA records clock64() at its pipeline events into
 // BwdArgs.dbg, [role][slot] = (tag << 48) | clock.  Used by scripts/timeline.py; compiled out of the product build.
 #ifdef FASN_TIMELINE
-#define TL_DECL(role) unsigned long long* tl_p = (a.dbg && kt == (int)a.dbg_x && bh == (int)a.dbg_y) ? a.dbg + (role) * 2048 : nullptr; int tl_i = 0;
+#define TL_DECL(role) unsigned long long* tl_p = (a.dbg && blockIdx.x == a.dbg_x) ? a.dbg + (role) * 2048 : nullptr; int tl_i = 0;   // one CTA, all of its items
 #define TL_ONLY(cond) do { if (!(cond)) tl_p = nullptr; } while (0)
 #define TL(tag) do { if (tl_p && tl_i < 2048) tl_p[tl_i++] = ((unsigned long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFull); } while (0)
 // Per-CTA record (every CTA, thread 0): [4 b] = globaltimer at entry, [4 b + 1] = at exit, [4 b + 2] = clock64 cycles in
@@ -74,11 +82,33 @@ template <int D> struct BwdCfg {
   static constexpr int TILE_BYTES = 128 * D * 2;
   static constexpr int BLK_BYTES = 128 * 128;
   static constexpr int DS_BYTES = 2 * BLK_BYTES;                  // dS^T: [2 q-blocks][128 kv rows][128 B]
-  static constexpr int NUM_BARS = 18;
+  static constexpr int NUM_BARS = 27;
   static constexpr int DQ_STAGE_BYTES = 128 * 32 * 4;             // dQ staging chunk: 128 rows x 32 fp32 columns
   // K, V, Q ring (2), dO (1), dS^T, dQ staging (2 chunks), LSE2 ring + delta ring (2 x 2 x 512 B), barriers, tmem slot
   static constexpr int SMEM_BYTES = 5 * TILE_BYTES + DS_BYTES + 2 * DQ_STAGE_BYTES + 4 * 512 + NUM_BARS * 8 + 16;
+  static_assert(SMEM_BYTES <= 232448, "shared memory per CTA");
 };
+
+// One work item = one 128-row K/V tile of one (batch, head) unit and the Q / dO tiles that can see it.
+struct BwdItem { int kt, k0, bh, b, h, hk, i_start, n_iter; };
+
+template <bool CAUSAL> FASN_DEVICE BwdItem bwd_decode(const BwdArgs& a, int lin, int nkv, int nq) {
+  BwdItem w;
+  const TileCoord tcd = decode_block((uint32_t)lin, nkv, a.B * a.H, a.sched_group);
+  w.kt = tcd.tile;
+  w.k0 = tcd.tile * 128;
+  w.bh = tcd.bh;
+  w.b = tcd.bh / a.H;
+  w.h = tcd.bh - w.b * a.H;
+  w.hk = (a.Hkv == 1) ? 0 : w.h;
+  w.i_start = 0;
+  if (CAUSAL) {
+    const int first_q = w.k0 - a.causal_off;           // first query row that sees key k0
+    w.i_start = first_q > 0 ? (first_q >> 7) : 0;
+  }
+  w.n_iter = nq - w.i_start;                           // <= 0: no query sees this K/V tile (dK = dV = 0)
+  return w;
+}
 
 // TMA reduce-add shared -> global (fp32 tile added into the tensor at L2), bulk async-group completion
 FASN_DEVICE void tma_reduce_add_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
@@ -113,35 +143,9 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   TL_CTA_BEGIN();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const TileCoord tcd = decode_block(blockIdx.x, (a.Skv + 127) >> 7, a.B * a.H, a.sched_group);
-  const int kt = tcd.tile;
-  const int k0 = kt * 128;
-  const int bh = tcd.bh;
-  const int b = bh / a.H;
-  const int h = bh - b * a.H;
-  const int hk = (a.Hkv == 1) ? 0 : h;
-
+  const int nkv = (a.Skv + 127) >> 7;
   const int nq = (a.Sq + 127) >> 7;
-  int i_start = 0;
-  if (CAUSAL) {
-    const int first_q = k0 - a.causal_off;           // first query row that sees key k0
-    i_start = first_q > 0 ? (first_q >> 7) : 0;
-  }
-  const int n_iter = nq - i_start;
-
-  if (n_iter <= 0) {
-    // no query sees this K/V tile: dK = dV = 0
-    if (threadIdx.x < 128) {
-      const int row = k0 + threadIdx.x;
-      if (row < a.Skv) {
-        uint4* pk = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(dk_view.ptr) + b * dk_view.sb + h * dk_view.sh + (long long)row * dk_view.ss);
-        uint4* pv = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(dv_view.ptr) + b * dv_view.sb + h * dv_view.sh + (long long)row * dv_view.ss);
-#pragma unroll
-        for (int i = 0; i < D / 8; ++i) { pk[i] = make_uint4(0, 0, 0, 0); pv[i] = make_uint4(0, 0, 0, 0); }
-      }
-    }
-    return;
-  }
+  const int total = nkv * a.B * a.H;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();      // 128B-swizzled tiles need 1024-byte alignment
@@ -154,10 +158,13 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   float* sLse = reinterpret_cast<float*>(sDQ + 2 * Cfg::DQ_STAGE_BYTES);   // [2][128]
   float* sDelta = sLse + 256;                                              // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
-  uint64_t* kv_full = bars + 0;
+  // Parities: barriers that complete once per Q tile are indexed by the CTA's running tile count g (over all its items),
+  // barriers that complete once per item by the count m of items with work.
+  uint64_t* k_full = bars + 0;     // per item
   uint64_t* q_full = bars + 1;     // [2]
   uint64_t* q_empty = bars + 3;    // [2]
   uint64_t* do_full = bars + 5;
+  uint64_t* v_free = bars + 6;     // per item: the TMA store of dV has read its staging tile (sV)
   uint64_t* do_empty = bars + 7;
   uint64_t* s_full = bars + 9;
   uint64_t* dp_full = bars + 10;
@@ -166,64 +173,95 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* ds_empty = bars + 13;
   uint64_t* dq_full = bars + 14;
   uint64_t* dq_empty = bars + 15;  // 128 arrivals
-  uint64_t* dkv_full = bars + 16;
-  uint64_t* dv_full = bars + 17;   // the last dV MMA has completed: the dV epilogue overlaps the last dQ / dK MMAs
+  uint64_t* dkv_full = bars + 16;  // per item: every MMA of the item has completed
+  uint64_t* dv_full = bars + 17;   // per item: the last dV MMA has completed: the dV epilogue overlaps the last dQ / dK MMAs
+  uint64_t* item_full = bars + 18; // [2]  work-item ring: the producer has published an item index
+  uint64_t* item_empty = bars + 20;// [2]  14 arrivals: the MMA warp, the store warp, the eight compute warps and the four reducer warps have read it
+  uint64_t* v_full = bars + 22;    // per item
+  uint64_t* dv_staged = bars + 23; // per item, 256 arrivals: dV is in its staging tile (sV)
+  uint64_t* dk_staged = bars + 24; // per item, 256 arrivals: dK is in its staging tile (the dS^T tile)
+  uint64_t* ds_free = bars + 25;   // per item: the TMA store of dK has read the dS^T tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + Cfg::NUM_BARS);
+  volatile int* sItem = reinterpret_cast<volatile int*>(tmem_slot + 2);   // [2]
 
   const float* lse2_ws = a.delta + (long long)a.B * a.H * a.Sqp;     // second half of the workspace: LSE_n * log2e
   if (warp == 12 && lane == 0) {
-    // The producer thread initialises the barriers itself and issues the first loads (K, V, Q / LSE2 / delta / dO of the
-    // first tile) at once, before the TMEM allocation and the CTA-wide sync below: they are pure pipeline fill otherwise.
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v); tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_dk); tma_prefetch_desc(&tm_dv); tma_prefetch_desc(&tm_dq);
-    mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    mbar_init(do_full, 1); mbar_init(do_empty, 1);
+    mbar_init(k_full, 1); mbar_init(v_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&item_full[i], 1); mbar_init(&item_empty[i], 14); }
+    mbar_init(do_full, 1); mbar_init(do_empty, 1); mbar_init(v_free, 1);
+    mbar_init(dv_staged, 256); mbar_init(dk_staged, 256); mbar_init(ds_free, 1);
     mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(p_full, 256); mbar_init(ds_full, 256); mbar_init(ds_empty, 1);
     mbar_init(dq_full, 1); mbar_init(dq_empty, 128); mbar_init(dkv_full, 1); mbar_init(dv_full, 1);
     fence_mbar_init();
     fence_proxy_async_smem();
-    mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
-#pragma unroll
-    for (int db = 0; db < DB; ++db) {
-      tma_load_4d(sK + db * BLK_BYTES, &tm_k, kv_full, db * 64, k0, hk, b);
-      tma_load_4d(sV + db * BLK_BYTES, &tm_v, kv_full, db * 64, k0, hk, b);
-    }
-    const int qi0 = i_start * 128;
-    mbar_arrive_expect_tx(&q_full[0], TILE_BYTES + 1024);
-#pragma unroll
-    for (int db = 0; db < DB; ++db) tma_load_4d(sQ + db * BLK_BYTES, &tm_q, &q_full[0], db * 64, qi0, h, b);
-    bulk_load_1d(sLse, lse2_ws + (long long)bh * a.Sqp + qi0, 512, &q_full[0]);
-    bulk_load_1d(sDelta, a.delta + (long long)bh * a.Sqp + qi0, 512, &q_full[0]);
-    mbar_arrive_expect_tx(do_full, TILE_BYTES);
-#pragma unroll
-    for (int db = 0; db < DB; ++db) tma_load_4d(sDO + db * BLK_BYTES, &tm_do, do_full, db * 64, qi0, h, b);
   }
   if (warp == 14) { tmem_alloc<512>(tmem_slot); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  uint32_t iters_done = 0;                    // timeline builds: Q tiles of all items of this CTA (thread 0)
+
+  // Every consumer role reads the next item index from the two-deep ring the producer publishes.
+  auto next_item = [&](uint32_t item_n) -> int {
+    const int si = item_n & 1;
+    mbar_wait(&item_full[si], (item_n >> 1) & 1);
+    const int lin = sItem[si];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&item_empty[si]);
+    return lin;
+  };
 
   if (warp >= 12) {
     setmaxnreg_dec<BwdRegs<D>::kOther>();
     if (warp == 12 && lane == 0) {
       // ---------------------------------------------------------------- TMA producer
-      const float* lse2 = lse2_ws;
-      for (int it = 1; it < n_iter; ++it) {     // K, V and the first Q / dO tile were issued before the CTA-wide sync
-        const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        const int qi0 = (i_start + it) * 128;
-        mbar_wait(&q_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&q_full[s], TILE_BYTES + 1024);
+      int lin = blockIdx.x;
+      uint32_t item_n = 0, m = 0, g = 0;     // items published, items with work, Q tiles loaded
+      TL_DECL(4)
+      while (true) {
+        const int si = item_n & 1;
+        if (item_n >= 2) mbar_wait(&item_empty[si], ((item_n >> 1) - 1) & 1);
+        sItem[si] = (lin < total) ? lin : -1;
+        mbar_arrive(&item_full[si]);             // release: the index is visible to whoever observes the phase
+        if (lin >= total) break;
+        const BwdItem w = bwd_decode<CAUSAL>(a, lin, nkv, nq);
+        lin = (int)gridDim.x + atomicAdd(a.sched, 1);      // the next item (its latency hides behind this item's loads)
+        ++item_n;
+        if (w.n_iter <= 0) continue;
+        for (int it = 0; it < w.n_iter; ++it, ++g) {
+          const int s = g & 1;
+          const uint32_t ph = (g >> 1) & 1;
+          const int qi0 = (w.i_start + it) * 128;
+          mbar_wait(&q_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&q_full[s], TILE_BYTES + 1024);
 #pragma unroll
-        for (int db = 0; db < DB; ++db) tma_load_4d(sQ + s * TILE_BYTES + db * BLK_BYTES, &tm_q, &q_full[s], db * 64, qi0, h, b);
-        bulk_load_1d(sLse + s * 128, lse2 + (long long)bh * a.Sqp + qi0, 512, &q_full[s]);
-        bulk_load_1d(sDelta + s * 128, a.delta + (long long)bh * a.Sqp + qi0, 512, &q_full[s]);
-        mbar_wait(do_empty, (it & 1) ^ 1);     // single dO buffer: free once dV of the previous tile has completed
-        mbar_arrive_expect_tx(do_full, TILE_BYTES);
+          for (int db = 0; db < DB; ++db) tma_load_4d(sQ + s * TILE_BYTES + db * BLK_BYTES, &tm_q, &q_full[s], db * 64, qi0, w.h, w.b);
+          bulk_load_1d(sLse + s * 128, lse2_ws + (long long)w.bh * a.Sqp + qi0, 512, &q_full[s]);
+          bulk_load_1d(sDelta + s * 128, a.delta + (long long)w.bh * a.Sqp + qi0, 512, &q_full[s]);
+          mbar_wait(do_empty, (g & 1) ^ 1);     // single dO buffer: free once dV of the previous tile has completed
+          mbar_arrive_expect_tx(do_full, TILE_BYTES);
 #pragma unroll
-        for (int db = 0; db < DB; ++db) tma_load_4d(sDO + db * BLK_BYTES, &tm_do, do_full, db * 64, qi0, h, b);
+          for (int db = 0; db < DB; ++db) tma_load_4d(sDO + db * BLK_BYTES, &tm_do, do_full, db * 64, qi0, w.h, w.b);
+          if (it == 0) {
+            // K / V of this item, after Q / dO of its first tile (their buffers are free earlier).  The last reader of sK is the dQ
+            // MMA of the previous item's last tile (tile g - 1 of this CTA); sV is the staging tile of the previous item's dV store.
+            TL(40);
+            if (g > 0) mbar_wait(dq_full, (g - 1) & 1);
+            TL(41);
+            mbar_arrive_expect_tx(k_full, TILE_BYTES);
+#pragma unroll
+            for (int db = 0; db < DB; ++db) tma_load_4d(sK + db * BLK_BYTES, &tm_k, k_full, db * 64, w.k0, w.hk, w.b);
+            if (m > 0) mbar_wait(v_free, (m - 1) & 1);
+            TL(42);
+            mbar_arrive_expect_tx(v_full, TILE_BYTES);
+#pragma unroll
+            for (int db = 0; db < DB; ++db) tma_load_4d(sV + db * BLK_BYTES, &tm_v, v_full, db * 64, w.k0, w.hk, w.b);
+          }
+        }
+        ++m;
       }
     } else if (warp == 13) {
       // ---------------------------------------------------------------- MMA issuer
@@ -251,94 +289,140 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           umma_ss(tm + tm_dst, umma_desc_join(a_lo + off, hi_desc), umma_desc_join(b_lo + off, hi_desc), idesc_kk, kb > 0 ? 1u : 0u);
         }
       };
+      uint32_t item_n = 0, m = 0, g0 = 0;      // items seen, items with work, Q tiles of the items before this one
       TL_DECL(0)
       TL_ONLY(lane == 0);
-      mbar_wait(kv_full, 0);
-      mbar_wait(&q_full[0], 0);
-      tc_fence_after();
-      TL(1);
-      if (elect_one()) {
-        issue_kmajor(TM_S, sb + oK + KM, sb + oQ + KM);
-        tc_commit(s_full);
-      }
-      __syncwarp();
-      mbar_wait(do_full, 0);
-      tc_fence_after();
-      if (elect_one()) { issue_kmajor(TM_DP, sb + oV + KM, sb + oDO + KM); tc_commit(dp_full); }
-      __syncwarp();
-      for (int it = 0; it < n_iter; ++it) {
-        asm volatile("" : "+r"(sb));
-        const int s = it & 1;
-        const int s1 = s ^ 1;
-        const uint32_t ph1 = ((it + 1) >> 1) & 1;
-        const bool more = it + 1 < n_iter;
-        // dV += P^T dO_i
-        mbar_wait(p_full, it & 1);
+      while (true) {
+        const int lin = next_item(item_n);
+        if (lin < 0) break;
+        ++item_n;
+        const BwdItem w = bwd_decode<CAUSAL>(a, lin, nkv, nq);
+        const int n_iter = w.n_iter;
+        if (n_iter <= 0) continue;
+        // First tile of the item.  S^T overwrites P^T of the previous item's last tile (its dV MMA was issued earlier on the same
+        // pipe); dP^T overwrites the previous item's last dQ, which the reducers must have drained.
+        mbar_wait(k_full, m & 1);
+        mbar_wait(&q_full[g0 & 1], (g0 >> 1) & 1);
         tc_fence_after();
-        TL(2);
+        TL(1);
         if (elect_one()) {
-#pragma unroll
-          for (int kb = 0; kb < 8; ++kb)
-            umma_ts(tm + TM_DV, tm + TM_S + (kb >> 2) * 64 + (kb & 3) * 8, umma_desc_join(sb + oDO + MN + kb * (2048 >> 4), hi_desc),
-                    idesc_dv, (it > 0 || kb > 0) ? 1u : 0u);
-          tc_commit(do_empty);         // dO_i is dead once dP^T_i (issued earlier) and dV_i have completed
-          if (!more) tc_commit(dv_full);
+          issue_kmajor(TM_S, sb + oK + KM, sb + oQ + KM + (g0 & 1) * TILE16);
+          tc_commit(s_full);
         }
         __syncwarp();
-        // S^T of the next Q tile (overwrites P^T: ordered behind the dV MMAs on the tensor pipe)
-        if (more) {
-          mbar_wait(&q_full[s1], ph1);
+        mbar_wait(v_full, m & 1);
+        mbar_wait(do_full, g0 & 1);
+        if (g0 > 0) mbar_wait(dq_empty, (g0 - 1) & 1);
+        tc_fence_after();
+        if (elect_one()) { issue_kmajor(TM_DP, sb + oV + KM, sb + oDO + KM); tc_commit(dp_full); }
+        __syncwarp();
+        for (int it = 0; it < n_iter; ++it) {
+          asm volatile("" : "+r"(sb));
+          const uint32_t g = g0 + it;
+          const int s = g & 1;
+          const int s1 = s ^ 1;
+          const uint32_t ph1 = ((g + 1) >> 1) & 1;
+          const bool more = it + 1 < n_iter;
+          // dV += P^T dO_i
+          mbar_wait(p_full, g & 1);
           tc_fence_after();
-          TL(3);
+          TL(2);
           if (elect_one()) {
-            issue_kmajor(TM_S, sb + oK + KM, sb + oQ + KM + s1 * TILE16);
-            tc_commit(s_full);
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb)
+              umma_ts(tm + TM_DV, tm + TM_S + (kb >> 2) * 64 + (kb & 3) * 8, umma_desc_join(sb + oDO + MN + kb * (2048 >> 4), hi_desc),
+                      idesc_dv, (it > 0 || kb > 0) ? 1u : 0u);
+            tc_commit(do_empty);         // dO_i is dead once dP^T_i (issued earlier) and dV_i have completed
+            if (!more) tc_commit(dv_full);
           }
           __syncwarp();
-        }
-        // dQ_i = dS K first (its consumers, the reducer warps, then drain TMEM while dK executes) ;  dK += dS^T Q_i
-        mbar_wait(ds_full, it & 1);
-        tc_fence_after();
-        TL(4);
-        if (elect_one()) {
-#pragma unroll
-          for (int kb = 0; kb < 8; ++kb)
-            umma_ss(tm + TM_DQ, umma_desc_join(sb + oDS + MN + kb * (2048 >> 4), hi_desc), umma_desc_join(sb + oK + MN + kb * (2048 >> 4), hi_desc),
-                    idesc_dq, kb > 0 ? 1u : 0u);
-          tc_commit(dq_full);
-        }
-        __syncwarp();
-        auto issue_dk = [&](int kb0, int kb1) {
-#pragma unroll
-          for (int kb = kb0; kb < kb1; ++kb) {
-            const uint32_t off = ((kb >> 2) * BLK_BYTES + (kb & 3) * 32) >> 4;
-            umma_ss(tm + TM_DK, umma_desc_join(sb + oDS + KM + off, hi_desc), umma_desc_join(sb + oQ + MN + s * TILE16 + kb * (2048 >> 4), hi_desc),
-                    idesc_dk, (it > 0 || kb > 0) ? 1u : 0u);
+          // S^T of the next Q tile (overwrites P^T: ordered behind the dV MMAs on the tensor pipe)
+          if (more) {
+            mbar_wait(&q_full[s1], ph1);
+            tc_fence_after();
+            TL(3);
+            if (elect_one()) {
+              issue_kmajor(TM_S, sb + oK + KM, sb + oQ + KM + s1 * TILE16);
+              tc_commit(s_full);
+            }
+            __syncwarp();
           }
-        };
-        constexpr int kSplit = FASN_BWD_DK_SPLIT;
-        if (elect_one()) issue_dk(0, more ? kSplit : 8);
-        __syncwarp();
-        // dP^T of the next tile reuses the dQ columns: wait until the reducers have drained dQ_i
-        if (more) {
-          mbar_wait(do_full, (it + 1) & 1);
-          TL(5);
-          mbar_wait(dq_empty, it & 1);
+          // dQ_i = dS K first (its consumers, the reducer warps, then drain TMEM while dK executes) ;  dK += dS^T Q_i
+          mbar_wait(ds_full, g & 1);
           tc_fence_after();
-          TL(6);
-          if (elect_one()) { issue_kmajor(TM_DP, sb + oV + KM, sb + oDO + KM); tc_commit(dp_full); }
+          TL(4);
+          if (elect_one()) {
+#pragma unroll
+            for (int kb = 0; kb < 8; ++kb)
+              umma_ss(tm + TM_DQ, umma_desc_join(sb + oDS + MN + kb * (2048 >> 4), hi_desc), umma_desc_join(sb + oK + MN + kb * (2048 >> 4), hi_desc),
+                      idesc_dq, kb > 0 ? 1u : 0u);
+            tc_commit(dq_full);
+          }
+          __syncwarp();
+          auto issue_dk = [&](int kb0, int kb1) {
+#pragma unroll
+            for (int kb = kb0; kb < kb1; ++kb) {
+              const uint32_t off = ((kb >> 2) * BLK_BYTES + (kb & 3) * 32) >> 4;
+              umma_ss(tm + TM_DK, umma_desc_join(sb + oDS + KM + off, hi_desc), umma_desc_join(sb + oQ + MN + s * TILE16 + kb * (2048 >> 4), hi_desc),
+                      idesc_dk, (it > 0 || kb > 0) ? 1u : 0u);
+            }
+          };
+          constexpr int kSplit = FASN_BWD_DK_SPLIT;
+          if (elect_one()) issue_dk(0, more ? kSplit : 8);
+          __syncwarp();
+          // dP^T of the next tile reuses the dQ columns: wait until the reducers have drained dQ_i
+          if (more) {
+            mbar_wait(do_full, (g + 1) & 1);
+            TL(5);
+            mbar_wait(dq_empty, g & 1);
+            tc_fence_after();
+            TL(6);
+            if (elect_one()) { issue_kmajor(TM_DP, sb + oV + KM, sb + oDO + KM); tc_commit(dp_full); }
+            __syncwarp();
+          }
+          if (elect_one()) {
+            if (more) issue_dk(kSplit, 8);
+            tc_commit(&q_empty[s]);      // Q_i, LSE2_i and delta_i stay valid until the compute warps are done with tile i
+                                         // (ds_full above) and the MMAs that read Q_i have completed
+            tc_commit(ds_empty);
+            if (!more) tc_commit(dkv_full);
+          }
           __syncwarp();
         }
-        if (elect_one()) {
-          if (more) issue_dk(kSplit, 8);
-          tc_commit(&q_empty[s]);      // Q_i, LSE2_i and delta_i stay valid until the compute warps are done with tile i
-                                       // (ds_full above) and the MMAs that read Q_i have completed
-          tc_commit(ds_empty);
+        g0 += n_iter; ++m;
+      }
+    } else if (warp == 15) {
+      // ---------------------------------------------------------------- epilogue stores
+      // dV / dK of an item leave through TMA stores from their staging tiles.  This warp issues them and waits until they have
+      // read shared memory, then hands the tiles on (sV to the producer, the dS^T tile to the compute warps of the next item):
+      // a compute thread that waited here kept its whole warp, and with it the dK epilogue, back by ~1500 cycles per item.
+      uint32_t item_n = 0, m = 0;
+      while (true) {
+        const int lin = next_item(item_n);
+        if (lin < 0) break;
+        ++item_n;
+        const BwdItem w = bwd_decode<CAUSAL>(a, lin, nkv, nq);
+        if (w.n_iter <= 0) continue;
+        mbar_wait(dv_staged, m & 1);
+        if (lane == 0) {
+#pragma unroll
+          for (int db = 0; db < DB; ++db) tma_store_4d(&tm_dv, sV + db * BLK_BYTES, db * 64, w.k0, w.h, w.b);
+          tma_store_commit();
+          tma_store_wait_read_all();
+          mbar_arrive(v_free);
         }
         __syncwarp();
+        mbar_wait(dk_staged, m & 1);
+        if (lane == 0) {
+#pragma unroll
+          for (int db = 0; db < DB; ++db) tma_store_4d(&tm_dk, sDS + db * BLK_BYTES, db * 64, w.k0, w.h, w.b);
+          tma_store_commit();
+          tma_store_wait_read_all();
+          mbar_arrive(ds_free);
+        }
+        __syncwarp();
+        ++m;
       }
-      if (elect_one()) tc_commit(dkv_full);
-      __syncwarp();
     }
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ dQ reducers
@@ -353,38 +437,49 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     constexpr int NCH = D / 32;                           // 32-column chunks per dQ tile
     uint8_t* const stage_row = sDQ + r * 128;
     const int rx = (r & 7) << 4;
+    uint32_t item_n = 0, g0 = 0;
     TL_DECL(3)
     TL_ONLY(threadIdx.x == 256);
-    for (int it = 0; it < n_iter; ++it) {
-      const int qi0 = (i_start + it) * 128;
-      mbar_wait(dq_full, it & 1);
-      tc_fence_after();
-      TL(30);
-      uint32_t v[D];
+    while (true) {
+      const int lin = next_item(item_n);
+      if (lin < 0) break;
+      ++item_n;
+      const BwdItem w = bwd_decode<CAUSAL>(a, lin, nkv, nq);
+      const int n_iter = w.n_iter, bh = w.bh;
+      if (n_iter <= 0) continue;
+      for (int it = 0; it < n_iter; ++it) {
+        const uint32_t g = g0 + it;
+        const int qi0 = (w.i_start + it) * 128;
+        mbar_wait(dq_full, g & 1);
+        tc_fence_after();
+        TL(30);
+        uint32_t v[D];
 #pragma unroll
-      for (int cb = 0; cb < NCH; ++cb) tmem_ld_x32(tmem_base + lane_off + TM_DQ + cb * 32, v + cb * 32);
-      tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(dq_empty);                                // the dQ columns may be overwritten by dP^T now
-      TL(31);
+        for (int cb = 0; cb < NCH; ++cb) tmem_ld_x32(tmem_base + lane_off + TM_DQ + cb * 32, v + cb * 32);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(dq_empty);                                // the dQ columns may be overwritten by dP^T now
+        TL(31);
 #pragma unroll
-      for (int hb = 0; hb < NCH / 2; ++hb) {                // 64 columns (both staging chunks) per round
-        if (threadIdx.x == 256) tma_store_wait_read<0>();   // the previous round's reduces have read both staging chunks
-        named_bar_sync(2, 128);
+        for (int hb = 0; hb < NCH / 2; ++hb) {                // 64 columns (both staging chunks) per round
+          if (threadIdx.x == 256) tma_store_wait_read<0>();   // the previous round's reduces have read both staging chunks
+          named_bar_sync(2, 128);
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch)
+          for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<uint4*>(stage_row + ch * Cfg::DQ_STAGE_BYTES + ((g << 4) ^ rx)) =
-                make_uint4(v[hb * 64 + ch * 32 + g * 4], v[hb * 64 + ch * 32 + g * 4 + 1], v[hb * 64 + ch * 32 + g * 4 + 2], v[hb * 64 + ch * 32 + g * 4 + 3]);
-        fence_proxy_async_smem();
-        named_bar_sync(3, 128);
-        if (threadIdx.x == 256) {
-          tma_reduce_add_4d(&tm_dq, sDQ, hb * 64, qi0, bh, 0);
-          tma_reduce_add_4d(&tm_dq, sDQ + Cfg::DQ_STAGE_BYTES, hb * 64 + 32, qi0, bh, 0);
-          tma_store_commit();
+            for (int gg = 0; gg < 8; ++gg)
+              *reinterpret_cast<uint4*>(stage_row + ch * Cfg::DQ_STAGE_BYTES + ((gg << 4) ^ rx)) =
+                  make_uint4(v[hb * 64 + ch * 32 + gg * 4], v[hb * 64 + ch * 32 + gg * 4 + 1], v[hb * 64 + ch * 32 + gg * 4 + 2], v[hb * 64 + ch * 32 + gg * 4 + 3]);
+          fence_proxy_async_smem();
+          named_bar_sync(3, 128);
+          if (threadIdx.x == 256) {
+            tma_reduce_add_4d(&tm_dq, sDQ, hb * 64, qi0, bh, 0);
+            tma_reduce_add_4d(&tm_dq, sDQ + Cfg::DQ_STAGE_BYTES, hb * 64 + 32, qi0, bh, 0);
+            tma_store_commit();
+          }
         }
       }
+      g0 += n_iter;
     }
     if (threadIdx.x == 256) tma_store_wait_read<0>();   // the staging chunks have been read; the L2 adds complete on their own before the grid ends
   } else {
@@ -394,6 +489,30 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int half = warp >> 2;
     const int r = quarter * 32 + lane;                     // kv row inside the tile (row layout: AUX loop, epilogue)
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const float2 c2 = make_float2(a.scale_log2, a.scale_log2);
+    uint32_t item_n = 0, m = 0, g0 = 0;                    // items seen, items with work, Q tiles of the items before this one
+    TL_DECL(1 + half)
+    TL_ONLY(threadIdx.x == 0 || threadIdx.x == 128);
+    while (true) {
+    const int lin = next_item(item_n);
+    if (lin < 0) break;
+    ++item_n;
+    const BwdItem w = bwd_decode<CAUSAL>(a, lin, nkv, nq);
+    const int k0 = w.k0, bh = w.bh, b = w.b, h = w.h, i_start = w.i_start, n_iter = w.n_iter;
+    TL(20);                                                // item fetched
+    if (n_iter <= 0) {
+      // no query sees this K/V tile: dK = dV = 0
+      if (threadIdx.x < 128) {
+        const int row = k0 + threadIdx.x;
+        if (row < a.Skv) {
+          uint4* pk = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(dk_view.ptr) + b * dk_view.sb + h * dk_view.sh + (long long)row * dk_view.ss);
+          uint4* pv = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(dv_view.ptr) + b * dv_view.sb + h * dv_view.sh + (long long)row * dv_view.ss);
+#pragma unroll
+          for (int i = 0; i < D / 8; ++i) { pk[i] = make_uint4(0, 0, 0, 0); pv[i] = make_uint4(0, 0, 0, 0); }
+        }
+      }
+      continue;
+    }
     const uint8_t* mask_bh = a.mask.ptr ? reinterpret_cast<const uint8_t*>(a.mask.ptr) + b * a.mask.sb + h * a.mask.sh : nullptr;
     // A mask that is broadcast over the query axis (key padding, (B|1, H|1, 1, S)) is one byte per key: a key is either
     // visible to every query or to none, which the fast path handles like a row beyond Skv.
@@ -401,9 +520,6 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t bh_global = a.bh_offset + bh;
     const uint32_t kvw = (uint32_t)((k0 + quarter * 32) >> 5);   // 32-key word index of this warp's kv rows
     const bool kv_tail = (k0 + 128 > a.Skv) || key_only_mask;   // this K/V tile (may) have rows that no query sees
-    TL_DECL(1 + half)
-    TL_ONLY(threadIdx.x == 0 || threadIdx.x == 128);
-    const float2 c2 = make_float2(a.scale_log2, a.scale_log2);
 
     if constexpr (!AUX) {
       // ---------------------------------------------------------------- fast kernels: quad layout
@@ -434,8 +550,9 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       uint8_t* const ds_base = sDS + half * BLK_BYTES + (quarter * 32 + g) * 128 + 4 * t4;
 
       for (int it = 0; it < n_iter; ++it) {
-        const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
+        const uint32_t gt = g0 + it;                        // running Q-tile count of this CTA: ring slot and barrier parities
+        const int s = gt & 1;
+        const uint32_t ph = (gt >> 1) & 1;
         const int qi0 = (i_start + it) * 128;
         const int qc0 = qi0 + half * 64;                   // first query column of this warp
         TL(10);
@@ -449,7 +566,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         // ---- P^T = 2^(S^T c - LSE2)
         mbar_wait(&q_full[s], ph);                         // LSE2 and delta of this tile have landed (same barrier as Q_i)
-        mbar_wait(s_full, it & 1);
+        mbar_wait(s_full, gt & 1);
         tc_fence_after();
         TL(11);
         float p[64];
@@ -517,10 +634,11 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const float2 d2 = *reinterpret_cast<const float2*>(del_s + 8 * c);
           nd[c] = make_float2(-d2.x, -d2.y);
         }
-        mbar_wait(dp_full, it & 1);
+        mbar_wait(dp_full, gt & 1);
         tc_fence_after();
         TL(13);
-        mbar_wait(ds_empty, (it & 1) ^ 1);  // MMAs of the previous iteration no longer read the dS^T tile
+        mbar_wait(ds_empty, (gt & 1) ^ 1);  // MMAs of the previous iteration no longer read the dS^T tile
+        if (it == 0 && m > 0) mbar_wait(ds_free, (m - 1) & 1);   // ... and the TMA store of the previous item's dK, staged in this tile, has read it
         TL(14);
 #pragma unroll
         for (int h16 = 0; h16 < 2; ++h16) {
@@ -573,8 +691,9 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       make_keep(i_start * 128 + half * 64);
 
       for (int it = 0; it < n_iter; ++it) {
-        const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
+        const uint32_t gt = g0 + it;                        // running Q-tile count of this CTA: ring slot and barrier parities
+        const int s = gt & 1;
+        const uint32_t ph = (gt >> 1) & 1;
         const int qi0 = (i_start + it) * 128;
         const int qc0 = qi0 + half * 64;                     // first query column of this thread
         // keep0 / keep1: bit c = keep decision for (query qc0 + c [+32], this thread's kv row); generated one
@@ -608,7 +727,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
         }
         mbar_wait(&q_full[s], ph);                           // LSE2 and delta of this tile have landed (same barrier as Q_i)
-        mbar_wait(s_full, it & 1);
+        mbar_wait(s_full, gt & 1);
         tc_fence_after();
         TL(11);
         float p[64];
@@ -664,10 +783,11 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         TL(12);
         if (it + 1 < n_iter) make_keep(qc0 + 128);            // next tile's keep bits, while dP^T is still in flight
         // ---- dS'^T = P^T o (Z dP^T - (1-p) delta)      (dS = dS' / (1-p); the factor is folded into the dK / dQ scales)
-        mbar_wait(dp_full, it & 1);
+        mbar_wait(dp_full, gt & 1);
         tc_fence_after();
         TL(13);
-        mbar_wait(ds_empty, (it & 1) ^ 1);  // MMAs of the previous iteration no longer read the dS^T tile
+        mbar_wait(ds_empty, (gt & 1) ^ 1);  // MMAs of the previous iteration no longer read the dS^T tile
+        if (it == 0 && m > 0) mbar_wait(ds_free, (m - 1) & 1);   // ... and the TMA store of the previous item's dK, staged in this tile, has read it
         TL(14);
         const float* del_s = sDelta + s * 128 + half * 64;
 #pragma unroll
@@ -719,16 +839,18 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
 
     // ------------------------------------------------------------------ dK, dV epilogue
-    // V is dead after the last dP^T, K after the last dQ: stage dV into sV as soon as the last dV MMA is done (the last
-    // dQ / dK MMAs are still running), then dK into sK (same swizzled [block][row][128 B] layout)
+    // V is dead after the last dP^T: stage dV into sV as soon as the last dV MMA is done (the last dQ / dK MMAs are still
+    // running), then dK into the dS^T tile, which is dead with the last MMA (same swizzled [block][row][128 B] layout) -- sK
+    // stays free for the K tile of the next item, which the producer loads while dK is drained.
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
 #ifndef FASN_BWD_SPLIT_EPI
 #define FASN_BWD_SPLIT_EPI 1
 #endif
-      if (which == 0 && FASN_BWD_SPLIT_EPI) mbar_wait(dv_full, 0); else mbar_wait(dkv_full, 0);
+      if (which == 0 && FASN_BWD_SPLIT_EPI) mbar_wait(dv_full, m & 1); else mbar_wait(dkv_full, m & 1);
       tc_fence_after();
-      uint8_t* stage = which == 0 ? sV : sK;
+      TL(21 + which);                                      // 21: last dV MMA done, 22: every MMA of the item done
+      uint8_t* stage = which == 0 ? sV : sDS;
       const uint32_t tm_src = which == 0 ? TM_DV : TM_DK;
       const float mul = which == 0 ? (DROPOUT ? a.inv_keep : 1.f) : a.scale;   // a.scale already carries 1/(1-p)
       constexpr int COLS = D / 2;                          // columns per thread (this warp's half)
@@ -751,23 +873,20 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
       fence_proxy_async_smem();
-      named_bar_sync(1, 256);
-      if (threadIdx.x == 0) {
-#pragma unroll
-        for (int db = 0; db < DB; ++db) {
-          if (which == 0) tma_store_4d(&tm_dv, sV + db * BLK_BYTES, db * 64, k0, h, b);
-          else            tma_store_4d(&tm_dk, sK + db * BLK_BYTES, db * 64, k0, h, b);
-        }
-        tma_store_commit();
-      }
+      mbar_arrive(which == 0 ? dv_staged : dk_staged);     // warp 15 issues the store
     }
-    if (threadIdx.x == 0) tma_store_wait_read_all();     // the staging tiles have been read; the global writes complete on their own
+    TL(23);                                                // dK staged, store issued
+    g0 += n_iter; ++m;
+    if (threadIdx.x == 0) iters_done += n_iter;
+    }   // items
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 14) tmem_dealloc<512>(tmem_base);
-  TL_CTA_END(n_iter);
+  // the last CTA to finish hands the work counter back at zero for the next launch that uses this slot
+  if (threadIdx.x == 0 && atomicAdd(a.sched + 1, 1) == (int)gridDim.x - 1) { a.sched[0] = 0; a.sched[1] = 0; __threadfence(); }
+  TL_CTA_END(iters_done);
 }
 
 }  // namespace
@@ -780,7 +899,7 @@ static cudaError_t launch_bwd_t2(const CUtensorMap& tq, const CUtensorMap& tk, c
   constexpr int smem = BwdCfg<D>::SMEM_BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  dim3 grid(((a.Skv + 127) / 128) * a.B * a.H, 1, 1);
+  dim3 grid(a.grid_ctas, 1, 1);      // persistent: one CTA per SM (or per work item when there are fewer)
   kern<<<grid, kBwdThreads, smem, stream>>>(tq, tk, tv, tdo, tdk, tdv, tdq, a, dk, dv);
   return cudaGetLastError();
 }

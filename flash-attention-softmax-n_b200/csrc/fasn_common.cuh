@@ -60,6 +60,8 @@ struct BwdArgs {
   PhiloxKey key;
   uint32_t bh_offset;
   int sched_group;        // units scheduled tile-major at the end of the launch (decode_block)
+  int* sched;             // work counters of the persistent kernel (see FwdArgs::sched)
+  int grid_ctas;          // CTAs to launch: min(SMs of the device, work items)
   unsigned long long* dbg;   // FASN_TIMELINE builds only: phase timeline buffer (see fasn_bwd.cu)
   unsigned int dbg_x, dbg_y;
 };

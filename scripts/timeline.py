@@ -1,7 +1,9 @@
 """Phase timeline of one backward CTA (needs libfasn_timeline.so: build.py --timeline).  Writes gpurun_out/timeline_<tag>.txt.
 Tags: MMA thread 1 S^T(0) issue, 2 p_full seen, 3 q_full(next) seen, 4 ds_full seen, 5 do_full(next) seen, 6 dq_empty seen;
 compute 10 iteration start, 11 S^T ready, 12 P^T stored, 13 dP^T ready, 14 dS buffer free, 15 dS stored;
-reducer 30 dQ ready, 31 dQ drained from TMEM."""
+reducer 30 dQ ready, 31 dQ drained from TMEM; persistent kernel: the CTA given as x is recorded over all of its items --
+compute 20 item fetched, 21 last dV MMA done, 22 every MMA of the item done, 23 dK staged; producer 40 first Q / dO tile of an
+item issued, 41 sK free (K load issued), 42 sV free (V load issued)."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "flash-attention-softmax-n_b200")]
@@ -12,7 +14,7 @@ from flash_attention_softmax_n import flash_attention_n, _native
 tag = sys.argv[1] if len(sys.argv) > 1 else "tl"
 x, y = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (4, 70)
 lib = _native.load()
-buf = torch.zeros(5 * 2048, dtype=torch.int64, device="cuda")
+buf = torch.zeros(5 * 2048 + 4 * 65536, dtype=torch.int64, device="cuda")   # role timelines + the per-CTA records behind them
 lib.fasn_set_timeline.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_uint]
 B, H, S, D = 4, 32, 4096, 128
 q, k, v = (torch.empty(B, H, S, D, device="cuda", dtype=torch.float16).normal_(0, 0.5).requires_grad_() for _ in range(3))
@@ -23,7 +25,7 @@ for i in range(3):
     o = flash_attention_n(q, k, v, softmax_n_param=0.5, is_causal=True, dropout_p=0.1, _philox=(1, i))
     o.backward(do)
 torch.cuda.synchronize()
-ev = buf.cpu().view(5, 2048)
+ev = buf.cpu()[:5 * 2048].view(5, 2048)
 rows = []
 for role in range(5):
     for e in ev[role].tolist():
