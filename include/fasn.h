@@ -22,7 +22,9 @@
  *     cudaError_t; fasn_last_error() returns a thread-local description of the last failure;
  *   - launches are asynchronous on `stream`; nothing here synchronises the device;
  *   - re-entrant.  Process-wide state, all mutex-guarded: the driver entry point looked up once (immutable), the
- *     fasn_profile event lists, and the device arena of fasn_attention_host (one per device, grown on demand).
+ *     fasn_profile event lists, the device arena of fasn_attention_host (one per device, grown on demand) and, per device,
+ *     a pool of work counters for the persistent kernels (one pair per launch, handed out round-robin; every kernel
+ *     leaves its pair at zero).
  */
 #ifndef FASN_H_
 #define FASN_H_
