@@ -29,10 +29,6 @@
 #include "fasn_common.cuh"
 #include "fasn_ptx.cuh"
 
-#ifndef FASN_FWD_ANTIPHASE
-#define FASN_FWD_ANTIPHASE 0     // 1: alternate the exponent phases of the two Q tiles at D = 64, 2: at both head dims
-#endif
-
 namespace fasn {
 
 namespace {
@@ -372,13 +368,6 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint8_t* const sOt = sO + (Cfg::SO_TILES == 2 ? t : 0) * TILE_BYTES;
     uint64_t* const so_bar = &so_done[Cfg::SO_TILES == 2 ? t : 0];
     uint32_t item_n = 0, sc = 0, kuses = 0;   // items seen, K/V steps of this Q tile so far, items that went through the epilogue
-    // Alternation of the exponent phases of the two Q tiles (FASN_FWD_ANTIPHASE): warp w of tile 0 and warp w + 4 of tile 1 run on
-    // the same scheduler and share its MUFU / ALU pipes.  Left alone they run in phase (both tiles start on S tiles issued back to
-    // back) and queue on the MUFU together, then idle together; a pair of named barriers per warp pair hands the exponent phase
-    // back and forth, so one warp of a scheduler computes exponentials while the other loads, takes its maximum and packs.
-    constexpr bool kAntiPhase = FASN_FWD_ANTIPHASE && (D == 64 || FASN_FWD_ANTIPHASE > 1);
-    const uint32_t ap_mine = 4 + (warp & 3) + 4 * t, ap_other = 4 + (warp & 3) + 4 * (t ^ 1);
-    if (kAntiPhase && t == 1) named_bar_arrive(ap_other, 64);     // tile 0 goes first
 
     while (true) {
       const int si = item_n & 1;
@@ -415,7 +404,6 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                                         : nullptr;
       const uint32_t bh_global = a.bh_offset + bh;
       const int n_t = (t == 0) ? w.n_tiles0 : w.n_tiles1;      // K/V tiles this Q tile needs
-      const int n_both = min(w.n_tiles0, w.n_tiles1);         // steps both Q tiles take: the ones that alternate
       // A mask broadcast over the query axis (key padding, row stride 0) without bias stays on the fast path: the 128 mask
       // bytes of a K/V tile are the same for every row, so each warp turns them into four 32-bit visibility words with
       // ballots and only tiles that contain a hidden key pay for the selects.
@@ -619,7 +607,6 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #endif
         constexpr int kPolyCount = (!FASN_DEBUG_FP32_P && (D == 64 || (DROPOUT && FASN_POLY_DROPOUT))) ? 1 : 0;
         const bool use_poly = kPolyCount > 0 && !generic && !masked_tile;
-        if (kAntiPhase && j < n_both) named_bar_sync(ap_mine, 64);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           if (use_poly) {
@@ -643,7 +630,6 @@ fasn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
           // P columns [32 hf, 32 hf + 32) <- keys [64 hf, 64 hf + 64): over S columns this thread has already read (D=128),
           // or in P_t's own columns once the previous P.V has consumed them (D=64)
-          if (kAntiPhase && hf == 1 && j < n_both) named_bar_arrive(ap_other, 64);   // the exponentials of this step are issued
           if (kSepP && hf == 0 && j > 0) { mbar_wait(&o_full[t], (sc + j - 1) & 1); tc_fence_after(); }
           tmem_st_x32((kSepP ? tmem_base + lane_off + 384 + t * 64 : tS) + hf * 32, pr + hf * 32);
 #if FASN_DEBUG_FP32_P
