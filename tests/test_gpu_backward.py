@@ -63,8 +63,9 @@ def test_backward_dropout_same_mask(fasn_lib, dtype, causal):
     kw = dict(softmax_n_param=0.5, is_causal=causal)
     got = run_fused(q, k, v, do, dropout_p=p, _philox=(seed, offset), **kw)
     want = oracle_all(q, k, v, do, keep_mask=keep, dropout_p=p, **kw)
-    for name, g, w in zip(("O", "dQ", "dK", "dV"), got, want):
-        check_close(name + "(dropout)", g, w, None, dtype, rel_scale=2.0)
+    native = native_lowp_all(q, k, v, do, keep_mask=keep, dropout_p=p, **kw)
+    for name, g, w, nat in zip(("O", "dQ", "dK", "dV"), got, want, native):
+        check_close(name + "(dropout)", g, w, nat, dtype, rel_scale=2.0)
 
 
 def test_backward_mask_bias_and_shared_kv(fasn_lib):
@@ -78,15 +79,17 @@ def test_backward_mask_bias_and_shared_kv(fasn_lib):
     kw = dict(softmax_n_param=2, scale=0.2, is_causal=True)
     got = run_fused(q, k, v, do, attn_mask=mask.cuda(), attn_bias=bias.cuda(), **kw)
     want = oracle_all(q, k, v, do, attn_mask=mask, attn_bias=bias.double(), **kw)
-    for name, a, b in zip(("O", "dQ", "dK", "dV"), got, want):
-        check_close(name + "(mask,bias)", a, b, None, dtype, rel_scale=1.5)
+    native = native_lowp_all(q, k, v, do, attn_mask=mask, attn_bias=bias, **kw)
+    for name, a, b, nat in zip(("O", "dQ", "dK", "dV"), got, want, native):
+        check_close(name + "(mask,bias)", a, b, nat, dtype, rel_scale=1.5)
     # shared K/V: gradients are summed over the heads
     q, k, v, do = make_qkv(2, 4, 130, 190, 64, dtype, seed=9, heads_kv=1)
     got = run_fused(q, k[:, 0], v[:, 0], do, softmax_n_param=1)
     want = oracle_all(q, k[:, 0], v[:, 0], do, softmax_n_param=1)
-    for name, a, b in zip(("O", "dQ", "dK", "dV"), got, want):
+    native = native_lowp_all(q, k[:, 0], v[:, 0], do, softmax_n_param=1)
+    for name, a, b, nat in zip(("O", "dQ", "dK", "dV"), got, want, native):
         assert a.shape == b.shape
-        check_close(name + "(shared kv)", a, b, None, dtype, rel_scale=2.0)
+        check_close(name + "(shared kv)", a, b, nat, dtype, rel_scale=2.0)
 
 
 def test_triton_alias_forward_backward(fasn_lib):
@@ -100,8 +103,9 @@ def test_triton_alias_forward_backward(fasn_lib):
         o = flash_attention_n_triton(qq, kk, vv, causal, 0.2, n)
         o.backward(do)
         want = oracle_all(q, k, v, do, softmax_n_param=n, scale=0.2, is_causal=causal)
-        for name, a, b in zip(("O", "dQ", "dK", "dV"), (o, qq.grad, kk.grad, vv.grad), want):
-            check_close(name + "(triton alias)", a, b, None, dtype, rel_scale=1.5)
+        native = native_lowp_all(q, k, v, do, softmax_n_param=n, scale=0.2, is_causal=causal)
+        for name, a, b, nat in zip(("O", "dQ", "dK", "dV"), (o, qq.grad, kk.grad, vv.grad), want, native):
+            check_close(name + "(triton alias)", a, b, nat, dtype, rel_scale=1.5)
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
@@ -140,8 +144,9 @@ def test_backward_key_padding_mask(fasn_lib, D, causal, with_bias):
         bias = torch.randn(H, L, S, generator=torch.Generator().manual_seed(5)).to(dtype)
     got = run_fused(q, k, v, do, attn_mask=mask.cuda(), attn_bias=None if bias is None else bias.cuda(), **kw)
     want = oracle_all(q, k, v, do, attn_mask=mask, attn_bias=None if bias is None else bias.double(), **kw)
-    for name, a, b in zip(("O", "dQ", "dK", "dV"), got, want):
-        check_close(name + "(key padding)", a, b, None, dtype, rel_scale=1.5)
+    native = native_lowp_all(q, k, v, do, attn_mask=mask, attn_bias=bias, **kw)
+    for name, a, b, nat in zip(("O", "dQ", "dK", "dV"), got, want, native):
+        check_close(name + "(key padding)", a, b, nat, dtype, rel_scale=1.5)
     # gradients of padded keys are exactly zero
     for bi, n in enumerate(lens.tolist()):
         assert float(got[2][bi, :, n:].abs().max() if n < S else 0.0) == 0.0
@@ -160,7 +165,8 @@ def test_alibi_slopes_equal_the_dense_bias(fasn_lib, B, H, L, S, D, causal, dtyp
     kw = dict(softmax_n_param=1.0, is_causal=causal)
     got = run_fused(q, k, v, do, _alibi_slopes=slopes.cuda(), **kw)
     want = oracle_all(q, k, v, do, attn_bias=bias, **kw)
-    for name, a, b in zip(("O", "dQ", "dK", "dV"), got, want):
-        check_close(name + "(alibi)", a, b, None, dtype, rel_scale=1.5)
+    native = native_lowp_all(q, k, v, do, attn_bias=bias.to(dtype), **kw)     # the dense bias rounded to the I/O dtype, as a caller would pass it
+    for name, a, b, nat in zip(("O", "dQ", "dK", "dV"), got, want, native):
+        check_close(name + "(alibi)", a, b, nat, dtype, rel_scale=1.5)
     with pytest.raises(ValueError):
         run_fused(q, k, v, do, _alibi_slopes=slopes.cuda(), attn_bias=bias.to(dtype).cuda(), **kw)

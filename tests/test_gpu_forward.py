@@ -97,7 +97,7 @@ def test_forward_mask_and_bias(fasn_lib, dtype):
     pad[0, ..., 200:] = False
     out2 = flash_attention_n(q, k, v, attn_mask=pad.cuda())
     want2 = orc.slow_attention_n(q.double().cpu(), k.double().cpu(), v.double().cpu(), attn_mask=pad)
-    check_close("O(padding mask)", out2, want2, None, dtype)
+    check_close("O(padding mask)", out2, want2, orc.slow_attention_n(q, k, v, attn_mask=pad.cuda()), dtype)
 
 
 def test_forward_shared_kv_heads(fasn_lib):
@@ -107,7 +107,7 @@ def test_forward_shared_kv_heads(fasn_lib):
     q, k, v, _ = make_qkv(2, 4, 130, 190, 64, dtype, seed=9, heads_kv=1)
     out = flash_attention_n(q, k[:, 0], v[:, 0], softmax_n_param=1)
     want = orc.slow_attention_n(q.double().cpu(), k[:, 0].double().cpu(), v[:, 0].double().cpu(), softmax_n_param=1)
-    check_close("O(shared kv)", out, want, None, dtype)
+    check_close("O(shared kv)", out, want, orc.slow_attention_n(q, k[:, 0], v[:, 0], softmax_n_param=1), dtype)
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
@@ -121,7 +121,8 @@ def test_forward_dropout_matches_oracle_with_same_mask(fasn_lib, dtype, causal):
     keep = orc.dropout_keep_mask(seed, offset, B, H, L, S, p)
     want = orc.slow_attention_n(q.double().cpu(), k.double().cpu(), v.double().cpu(), softmax_n_param=0.5,
                                 is_causal=causal, keep_mask=keep, dropout_p=p)
-    check_close("O(dropout)", out, want, None, dtype, rel_scale=1.5)
+    native = orc.slow_attention_n(q, k, v, softmax_n_param=0.5, is_causal=causal, keep_mask=keep.cuda(), dropout_p=p)
+    check_close("O(dropout)", out, want, native, dtype, rel_scale=1.5)
     out_b = flash_attention_n(q, k, v, softmax_n_param=0.5, dropout_p=p, is_causal=causal, _philox=(seed, offset + 1))
     assert not torch.equal(out, out_b)
 
@@ -135,7 +136,7 @@ def test_forward_strided_inputs_and_errors(fasn_lib):
     q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))              # (B,H,L,D) views, row stride 3*H*D
     out = flash_attention_n(q, k, v, softmax_n_param=1, is_causal=True)
     want = orc.slow_attention_n(q.double().cpu(), k.double().cpu(), v.double().cpu(), softmax_n_param=1, is_causal=True)
-    check_close("O(strided)", out, want, None, dtype)
+    check_close("O(strided)", out, want, orc.slow_attention_n(q, k, v, softmax_n_param=1, is_causal=True), dtype)
     with pytest.raises(NotImplementedError):
         flash_attention_n(q.double(), k.double(), v.double())                    # float64: use slow_attention_n
     with pytest.raises(NotImplementedError):
@@ -149,7 +150,7 @@ def test_forward_strided_inputs_and_errors(fasn_lib):
 def test_other_head_dims_are_zero_padded(fasn_lib, E, Ev):
     """Head dims other than 64 / 128 (the Triton path's 16 / 32, flash_attn_triton.py:266) and Ev != E (README.md:50) run
     zero-padded to the next supported size; results and gradients equal the oracle's on the unpadded tensors."""
-    from tests._util import run_fused, oracle_all
+    from tests._util import run_fused, oracle_all, native_lowp_all
     dtype = torch.bfloat16
     B, H, L, S = 2, 2, 150, 210
     g = torch.Generator().manual_seed(E * 131 + Ev)
@@ -160,22 +161,24 @@ def test_other_head_dims_are_zero_padded(fasn_lib, E, Ev):
     kw = dict(softmax_n_param=1.0, is_causal=True)
     got = run_fused(q, k, v, do, **kw)
     want = oracle_all(q, k, v, do, **kw)
-    for name, a, b in zip(("O", "dQ", "dK", "dV"), got, want):
+    native = native_lowp_all(q, k, v, do, **kw)
+    for name, a, b, nat in zip(("O", "dQ", "dK", "dV"), got, want, native):
         assert a.shape == b.shape, (name, a.shape, b.shape)
-        check_close(f"{name}(E={E},Ev={Ev})", a, b, None, dtype, rel_scale=1.5)
+        check_close(f"{name}(E={E},Ev={Ev})", a, b, nat, dtype, rel_scale=1.5)
 
 
 @pytest.mark.parametrize("scale", [-0.2, 0.0])
 def test_forward_backward_non_positive_scale(fasn_lib, scale):
     """A non-positive logit scale takes the generic (pre-scaling) path: the running max must follow the scaled scores."""
-    from tests._util import run_fused, oracle_all
+    from tests._util import run_fused, oracle_all, native_lowp_all
     dtype = torch.float16
     q, k, v, do = make_qkv(1, 2, 200, 264, 64, dtype, seed=41)
     kw = dict(softmax_n_param=1.0, scale=scale, is_causal=True)
     got = run_fused(q, k, v, do, **kw)
     want = oracle_all(q, k, v, do, **kw)
-    for name, a, b in zip(("O", "dQ", "dK", "dV"), got, want):
-        check_close(f"{name}(scale={scale})", a, b, None, dtype, rel_scale=1.5)
+    native = native_lowp_all(q, k, v, do, **kw)
+    for name, a, b, nat in zip(("O", "dQ", "dK", "dV"), got, want, native):
+        check_close(f"{name}(scale={scale})", a, b, nat, dtype, rel_scale=1.5)
 
 
 def test_forward_long_sequence_rows(fasn_lib):
@@ -191,4 +194,5 @@ def test_forward_long_sequence_rows(fasn_lib):
     for lo, hi in ((0, 128), (S - 128, S), (30000, 30100)):
         want = orc.slow_attention_n(q[:, :, lo:hi].double().cpu(), k[:, :, :hi].double().cpu(), v[:, :, :hi].double().cpu(),
                                     softmax_n_param=1.0, is_causal=True)
-        check_close(f"O[{lo}:{hi}]", out[:, :, lo:hi], want, None, dtype)
+        native = orc.slow_attention_n(q[:, :, lo:hi], k[:, :, :hi], v[:, :, :hi], softmax_n_param=1.0, is_causal=True)
+        check_close(f"O[{lo}:{hi}]", out[:, :, lo:hi], want, native, dtype)

@@ -46,8 +46,11 @@ def test_full_size_units_match_oracle(c3, b, h):
     keep = orc.dropout_keep_mask(SEED, OFFSET, 1, 1, S, S, P_DROP, bh_offset=b * H + h)
     want = orc.attention_fwd_bwd(sl(c3["q"]), sl(c3["k"]), sl(c3["v"]), sl(c3["do"]), softmax_n_param=N_PARAM,
                                  is_causal=True, keep_mask=keep, dropout_p=P_DROP)
-    for name, got, ref in zip(("O", "dQ", "dK", "dV"), (c3["o"], c3["dq"], c3["dk"], c3["dv"]), want):
-        check_close(f"{name}[{b},{h}]", sl(got), ref, None, torch.float16, rel_scale=2.0)
+    dev = lambda t: t[b:b + 1, h:h + 1]
+    native = orc.attention_fwd_bwd(dev(c3["q"]), dev(c3["k"]), dev(c3["v"]), dev(c3["do"]), dtype=torch.float16, softmax_n_param=N_PARAM,
+                                   is_causal=True, keep_mask=keep.cuda(), dropout_p=P_DROP)
+    for name, got, ref, nat in zip(("O", "dQ", "dK", "dV"), (c3["o"], c3["dq"], c3["dk"], c3["dv"]), want, native):
+        check_close(f"{name}[{b},{h}]", sl(got), ref, nat, torch.float16, rel_scale=2.0)
 
 
 def test_forward_is_deterministic_and_shard_invariant(c3):
