@@ -257,6 +257,7 @@ int fasn_fwd(const FasnParams* p) {
     int num_sms = 0;
     if (int rc = sched_slot(&a.sched, &num_sms)) return rc;
     const long long items = (long long)B * H * ((L + 255) / 256);
+    if (items > 0x7FFFFFFFll) return fail(FASN_EUNSUPPORTED, "more than 2^31-1 forward work items (batch x heads x 256-row blocks) per call");
     a.grid_ctas = (int)(items < num_sms ? items : num_sms);
   }
 #ifdef FASN_TIMELINE
@@ -328,6 +329,7 @@ int fasn_bwd(const FasnParams* p) {
     int num_sms = 0;
     if (int rc = sched_slot(&a.sched, &num_sms)) return rc;
     const long long items = (long long)B * H * ((S + 127) / 128);
+    if (items > 0x7FFFFFFFll) return fail(FASN_EUNSUPPORTED, "more than 2^31-1 backward work items (batch x heads x 128-row K/V tiles) per call");
     a.grid_ctas = (int)(items < num_sms ? items : num_sms);
   }
 #ifdef FASN_TIMELINE
