@@ -844,10 +844,7 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // stays free for the K tile of the next item, which the producer loads while dK is drained.
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-#ifndef FASN_BWD_SPLIT_EPI
-#define FASN_BWD_SPLIT_EPI 1
-#endif
-      if (which == 0 && FASN_BWD_SPLIT_EPI) mbar_wait(dv_full, m & 1); else mbar_wait(dkv_full, m & 1);
+      mbar_wait(which == 0 ? dv_full : dkv_full, m & 1);
       tc_fence_after();
       TL(21 + which);                                      // 21: last dV MMA done, 22: every MMA of the item done
       uint8_t* stage = which == 0 ? sV : sDS;
