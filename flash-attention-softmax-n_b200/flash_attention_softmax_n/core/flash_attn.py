@@ -253,6 +253,10 @@ def flash_attention_n(
         alibi = _alibi_slopes.detach().to(device=query.device, dtype=torch.float32).contiguous()
     seed, offset = (0, 0)
     if dropout_p > 0.0:
+        if _philox is None and torch.cuda.is_current_stream_capturing():
+            # (seed, offset) are host integers in the kernel arguments: a captured graph would replay ONE dropout mask for ever
+            raise RuntimeError("flash_attention_n with dropout_p > 0 cannot be captured into a CUDA graph: the dropout stream "
+                               "(seed, offset) is drawn on the host per call; capture with dropout_p = 0 or run this call eagerly")
         seed, offset = _philox if _philox is not None else _next_philox(query.device)
     out = _FusedAttentionN.apply(query, key, value, heads_kv, n, sm_scale, bool(is_causal), float(dropout_p),
                                  mask, bias, int(seed), int(offset), int(_bh_offset), alibi)
