@@ -296,8 +296,16 @@ int fasn_bwd(const FasnParams* p) {
   if (int rc = make_map(&tk, p->k.ptr, p->k.stride_b, p->k.stride_h, p->k.stride_s, B, Hkv, S, D, bf16, "k")) return rc;
   if (int rc = make_map(&tv, p->v.ptr, p->v.stride_b, p->v.stride_h, p->v.stride_s, B, Hkv, S, D, bf16, "v")) return rc;
   if (int rc = make_map(&tdo, p->dout.ptr, p->dout.stride_b, p->dout.stride_h, p->dout.stride_s, B, H, L, D, bf16, "dout")) return rc;
-  if (int rc = make_map(&tdk, p->dk.ptr, p->dk.stride_b, p->dk.stride_h, p->dk.stride_s, B, H, S, D, bf16, "dk")) return rc;
-  if (int rc = make_map(&tdv, p->dv.ptr, p->dv.stride_b, p->dv.stride_h, p->dv.stride_s, B, H, S, D, bf16, "dv")) return rc;
+  const bool head_sum = p->dk_accum != nullptr || p->dv_accum != nullptr;
+  if (head_sum) {
+    if (p->dk_accum == nullptr || p->dv_accum == nullptr) return fail(FASN_EINVAL, "dk_accum and dv_accum come as a pair");
+    if (Hkv != 1) return fail(FASN_EINVAL, "dk_accum / dv_accum are for shared K/V (heads_kv == 1)");
+    if ((reinterpret_cast<uintptr_t>(p->dk_accum) | reinterpret_cast<uintptr_t>(p->dv_accum)) & 15) return fail(FASN_EINVAL, "dk_accum / dv_accum must be 16-byte aligned");
+    tdk = tq; tdv = tq;      // never used: the kernel adds into the accumulators instead of storing dk / dv
+  } else {
+    if (int rc = make_map(&tdk, p->dk.ptr, p->dk.stride_b, p->dk.stride_h, p->dk.stride_s, B, H, S, D, bf16, "dk")) return rc;
+    if (int rc = make_map(&tdv, p->dv.ptr, p->dv.stride_b, p->dv.stride_h, p->dv.stride_s, B, H, S, D, bf16, "dv")) return rc;
+  }
   if (p->o.ptr == nullptr) return fail(FASN_EINVAL, "o is null");
   // the delta pre-pass reads O and dO with 16-byte loads
   if ((reinterpret_cast<uintptr_t>(p->o.ptr) & 15) != 0 || (p->o.stride_s % 8) != 0 || (p->o.stride_h % 8) != 0 || (p->o.stride_b % 8) != 0)
@@ -318,6 +326,7 @@ int fasn_bwd(const FasnParams* p) {
   a.bias = aux_view(p->bias);
   a.alibi = p->alibi_slopes;
   a.dbias = fasn::AuxView{p->dbias, p->dbias_stride_b, p->dbias_stride_h, p->dbias_stride_q};
+  a.dk_accum = p->dk_accum; a.dv_accum = p->dv_accum;
   if (p->dbias != nullptr && p->bias.ptr == nullptr && p->alibi_slopes == nullptr && !(p->mask.ptr != nullptr && p->mask.stride_q != 0))
     return fail(FASN_EINVAL, "dbias is produced by the dense-tensor kernels: pass the bias (or ALiBi slopes / a dense mask) it belongs to");
   a.drop_thr = keep_threshold(p->dropout_p);

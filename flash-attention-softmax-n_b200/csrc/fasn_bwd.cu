@@ -403,21 +403,26 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         ++item_n;
         const BwdItem w = bwd_decode<CAUSAL>(a, lin, nkv, nq);
         if (w.n_iter <= 0) continue;
+        const bool head_sum = a.dk_accum != nullptr;     // shared K/V: the compute warps added dK / dV into the accumulators themselves
         mbar_wait(dv_staged, m & 1);
         if (lane == 0) {
+          if (!head_sum) {
 #pragma unroll
-          for (int db = 0; db < DB; ++db) tma_store_4d(&tm_dv, sV + db * BLK_BYTES, db * 64, w.k0, w.h, w.b);
-          tma_store_commit();
-          tma_store_wait_read_all();
+            for (int db = 0; db < DB; ++db) tma_store_4d(&tm_dv, sV + db * BLK_BYTES, db * 64, w.k0, w.h, w.b);
+            tma_store_commit();
+            tma_store_wait_read_all();
+          }
           mbar_arrive(v_free);
         }
         __syncwarp();
         mbar_wait(dk_staged, m & 1);
         if (lane == 0) {
+          if (!head_sum) {
 #pragma unroll
-          for (int db = 0; db < DB; ++db) tma_store_4d(&tm_dk, sDS + db * BLK_BYTES, db * 64, w.k0, w.h, w.b);
-          tma_store_commit();
-          tma_store_wait_read_all();
+            for (int db = 0; db < DB; ++db) tma_store_4d(&tm_dk, sDS + db * BLK_BYTES, db * 64, w.k0, w.h, w.b);
+            tma_store_commit();
+            tma_store_wait_read_all();
+          }
           mbar_arrive(ds_free);
         }
         __syncwarp();
@@ -501,8 +506,8 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const int k0 = w.k0, bh = w.bh, b = w.b, h = w.h, i_start = w.i_start, n_iter = w.n_iter;
     TL(20);                                                // item fetched
     if (n_iter <= 0) {
-      // no query sees this K/V tile: dK = dV = 0
-      if (threadIdx.x < 128) {
+      // no query sees this K/V tile: dK = dV = 0 (nothing to add when the heads are summed into zero-filled accumulators)
+      if (threadIdx.x < 128 && a.dk_accum == nullptr) {
         const int row = k0 + threadIdx.x;
         if (row < a.Skv) {
           uint4* pk = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(dk_view.ptr) + b * dk_view.sb + h * dk_view.sh + (long long)row * dk_view.ss);
@@ -851,11 +856,26 @@ fasn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const uint32_t tm_src = which == 0 ? TM_DV : TM_DK;
       const float mul = which == 0 ? (DROPOUT ? a.inv_keep : 1.f) : a.scale;   // a.scale already carries 1/(1-p)
       constexpr int COLS = D / 2;                          // columns per thread (this warp's half)
+      // Shared K/V (3-D key / value: one K/V head serves every query head): dK / dV of all heads of a batch element belong to the
+      // same rows, so they are added into float32 accumulators with 16-byte reductions at the L2 instead of being written per
+      // head for the host to sum (H times the memory and a pass over it).  Off the headline path: taken only when the caller
+      // passes the accumulators.
+      float* const acc = which == 0 ? a.dv_accum : a.dk_accum;
+      float* const acc_row = acc ? acc + ((long long)b * a.Skv + (k0 + r)) * D + half * COLS : nullptr;
 #pragma unroll
       for (int cb = 0; cb < COLS / 32; ++cb) {
         uint32_t v[32];
         tmem_ld_x32(tmem_base + lane_off + tm_src + half * COLS + cb * 32, v);
         tmem_wait_ld();
+        if (acc != nullptr) {
+          if (k0 + r < a.Skv) {
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4)
+              red_add_v4(acc_row + cb * 32 + g4 * 4, __uint_as_float(v[g4 * 4]) * mul, __uint_as_float(v[g4 * 4 + 1]) * mul,
+                         __uint_as_float(v[g4 * 4 + 2]) * mul, __uint_as_float(v[g4 * 4 + 3]) * mul);
+          }
+          continue;
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 w;

@@ -54,6 +54,8 @@ struct BwdArgs {
   AuxView mask, bias;
   const float* alibi;     // H slopes or null (generic kernels)
   AuxView dbias;          // optional output of the dense-tensor kernels: dS in the I/O dtype (const-ness of AuxView::ptr is cast away)
+  float* dk_accum;        // shared K/V (Hkv == 1), optional: (B,1,Skv,D) fp32 accumulators the kernel adds every head's dK / dV into
+  float* dv_accum;        //   (zero-filled by the caller); null = per-head dK / dV tensors through TMA stores
   uint32_t drop_thr;
   float inv_keep;         // 1 / P(keep)
   float keep_prob;        // P(keep) = T / 256

@@ -14,7 +14,7 @@ from typing import Optional
 
 import torch
 
-FASN_ABI_VERSION = 2
+FASN_ABI_VERSION = 3
 FASN_FP16, FASN_BF16 = 0, 1
 
 _LIB_ENV = "FASN_LIBRARY"
@@ -49,6 +49,7 @@ class FasnParams(ctypes.Structure):
         ("dbias", ctypes.c_void_p), ("dbias_stride_b", ctypes.c_int64), ("dbias_stride_h", ctypes.c_int64),
         ("dbias_stride_q", ctypes.c_int64),
         ("o_f32", ctypes.c_void_p),
+        ("dk_accum", ctypes.c_void_p), ("dv_accum", ctypes.c_void_p),
     ]
 
 

@@ -124,14 +124,24 @@ class _FusedAttentionN(torch.autograd.Function):
         Lp = (L + 127) // 128 * 128
         with torch.cuda.device(q.device):
             dq = torch.empty((B, H, L, D), dtype=q.dtype, device=q.device)
-            # dK / dV are produced per query head; shared K/V (heads_kv == 1) are reduced over heads below
-            dk = torch.empty((B, H, S, D), dtype=q.dtype, device=q.device)
-            dv = torch.empty((B, H, S, D), dtype=q.dtype, device=q.device)
+            # dK / dV are produced per query head; with shared K/V (heads_kv == 1) the kernel adds every head's contribution
+            # into float32 (B,1,S,D) accumulators instead (FasnParams.dk_accum / dv_accum)
+            head_sum = heads_kv == 1 and H > 1
+            if head_sum:
+                dk_acc = torch.zeros((B, 1, S, D), dtype=torch.float32, device=q.device)
+                dv_acc = torch.zeros((B, 1, S, D), dtype=torch.float32, device=q.device)
+            else:
+                dk = torch.empty((B, H, S, D), dtype=q.dtype, device=q.device)
+                dv = torch.empty((B, H, S, D), dtype=q.dtype, device=q.device)
             ws = torch.empty((2, B, H, Lp), dtype=torch.float32, device=q.device)
             dq_accum = torch.empty((B, H, Lp, D), dtype=torch.float32, device=q.device)
             p = _native.FasnParams()
             _fill_common(p, q, k, v, o, lse, heads_kv, n, scale, causal, dropout_p, seed, offset, bh_offset, mask, bias, alibi)
-            p.dout, p.dq, p.dk, p.dv = (_native.tensor_view(t) for t in (do, dq, dk, dv))
+            p.dout, p.dq = _native.tensor_view(do), _native.tensor_view(dq)
+            if head_sum:
+                p.dk_accum, p.dv_accum = dk_acc.data_ptr(), dv_acc.data_ptr()
+            else:
+                p.dk, p.dv = _native.tensor_view(dk), _native.tensor_view(dv)
             p.delta, p.dq_accum = ws.data_ptr(), dq_accum.data_ptr()
             ds = None
             if bias is not None and ctx.needs_input_grad[9]:
@@ -139,9 +149,8 @@ class _FusedAttentionN(torch.autograd.Function):
                 ds = torch.zeros((B, H, L, S), dtype=q.dtype, device=q.device)
                 p.dbias, p.dbias_stride_b, p.dbias_stride_h, p.dbias_stride_q = ds.data_ptr(), H * L * S, L * S, S
             _native.check(lib.fasn_bwd(ctypes.byref(p)), "fasn_bwd")
-        if heads_kv == 1 and H > 1:
-            dk = dk.sum(dim=1, keepdim=True, dtype=torch.float32).to(q.dtype)
-            dv = dv.sum(dim=1, keepdim=True, dtype=torch.float32).to(q.dtype)
+        if head_sum:
+            dk, dv = dk_acc.to(q.dtype), dv_acc.to(q.dtype)
         dbias = None
         if ds is not None:
             # reduce over the axes the bias broadcasts (size 1), accumulating in float32

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define FASN_ABI_VERSION 2
+#define FASN_ABI_VERSION 3
 
 enum { FASN_FP16 = 0, FASN_BF16 = 1 };
 
@@ -76,7 +76,7 @@ typedef struct FasnParams {
 
   /* backward only */
   FasnTensor dout;        /* dL/dO                                                                      */
-  FasnTensor dq, dk, dv;  /* outputs; dk, dv are per QUERY head (B,H,S,D) even when heads_kv == 1       */
+  FasnTensor dq, dk, dv;  /* outputs; dk, dv are per QUERY head (B,H,S,D) even when heads_kv == 1 (but see dk_accum) */
   float*     delta;       /* workspace 2 x (B,H,Lp) fp32 (delta, then LSE*log2e), Lp = L rounded up to 128 */
   float*     dq_accum;    /* workspace (B,H,Lp,D) fp32; fasn_bwd zero-fills it itself                   */
 
@@ -109,6 +109,12 @@ typedef struct FasnParams {
   /* forward, debug library only (libfasn_debug32.so, built with -DFASN_DEBUG_FP32_P=1: P as two 16-bit terms, float32 output):
    * contiguous (B,H,L,D) float32 copy of the output, or NULL.  The product library rejects a non-NULL value. */
   float*  o_f32;
+
+  /* backward only, optional, heads_kv == 1 (K/V shared by all heads): float32 accumulators (B,1,S,D), contiguous, ZERO-FILLED BY THE
+   * CALLER.  When both are given the kernel adds every query head's dK / dV (already scaled) into them with vector reductions at
+   * the L2 instead of writing per-head (B,H,S,D) tensors for the caller to sum; `dk` / `dv` are then not written and may be null. */
+  float*  dk_accum;
+  float*  dv_accum;
 } FasnParams;
 
 /* ABI version of the loaded library (== FASN_ABI_VERSION it was built with). */
